@@ -1,0 +1,567 @@
+// kernel_template.cuh — hand-written sm_100a kernels of the batched interior-point MCP solver.
+//
+// This file is NOT compiled on its own: plan.cpp prepends a generated prologue (problem-size macros,
+// assembly tables as __device__ const arrays, and the device functions mcp_eval_newton / mcp_eval_sens
+// lowered from the traced G, H and Jacobian entries) and hands the result to NVRTC for sm_100a.
+//
+// One WARP owns one problem instance for its whole solve (persistent over Newton iterations): the
+// iterate (x, y, s), residuals, Jacobian entries and the active window of the banded factorisation live
+// in shared memory; HBM is touched for θ/x₀/y₀/s₀ in, (x, y, s, …) out, and an L2-resident scratch that
+// streams the banded condensed matrix into the window and the finished U rows out of it.
+//
+// Reference semantics restated here (file:line in /root/reference):
+//   Newton / ϵ-homotopy loop            src/solver.jl:63-121
+//   regularised KKT solve               src/solver.jl:79-83   (∇F + tol·I) δz = −F
+//   fraction-to-the-boundary linesearch src/solver.jl:93-94,127-138
+//   IFT sensitivities                   src/AutoDiff.jl:18-40,59-76,98
+//
+// Macros provided by the prologue:
+//   NX NY NT NRED KL KU WC WR WS1 WSS NRHS_SENS NJV NJTV ND THETA_IN_SMEM
+//   SOLVE_WARPS SENS_WARPS  SOLVE_SMEM_DOUBLES SENS_SMEM_DOUBLES (per warp)
+//   SOLVE_SCRATCH SENS_SCRATCH (doubles per warp)  HAS_JT
+// Tables: D_RC D_TP (dests), T_COEF T_A T_B T_K (terms), R_GROW R_PTR R_CODE R_K R_COEF (rhs),
+//   H_PTR H_CODE H_COL H_COEF (H_x rows), PERM, Q_PTR Q_ROW Q_CODE Q_COEF (θ-Jacobian by column)
+
+#define FULLMASK 0xffffffffu
+
+struct SolveParams {
+  long long B;
+  const double* theta;
+  const double* x0;
+  const double* y0;
+  const double* s0;
+  double* x_out;
+  double* y_out;
+  double* s_out;
+  double* kkt_out;
+  double* eps_out;
+  int* outer_out;
+  int* status_out;
+  int* steps_out;
+  double* scratch;
+  unsigned long long* counters;  // [0] work queue, [1] Σ newton steps, [2] # solved
+  double tol;
+  double tightening_rate;
+  double loosening_rate;
+  double min_stepsize;
+  int max_inner;
+  int max_outer;
+};
+
+struct SensParams {
+  long long B;
+  const double* theta;
+  const double* x;
+  const double* y;
+  const double* s;
+  double* dzdtheta;        // [n x NT x B] or null
+  const double* zbar;      // [n x B] or null
+  double* thetabar;        // [NT x B] or null
+  const double* theta_p;   // [NT x P x B] or null
+  double* z_p;             // [n x P x B] or null
+  int* status_out;         // or null
+  double* scratch;
+  unsigned long long* counters;
+  int P;
+};
+
+__device__ __forceinline__ double opval(int code, const double* __restrict__ jv, const double* __restrict__ th) {
+  return code >= 0 ? jv[code] : (code == -1 ? 1.0 : th[-2 - code]);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+
+// NaN-propagating max, like Julia's norm(F, Inf) (src/solver.jl:107)
+__device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
+
+__device__ __forceinline__ double warp_nanmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULLMASK, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Assembly of the condensed matrix C = G_x + tol·I − G_y D⁻¹ H_x into banded global rows.
+// Cg: NRED rows × WS doubles; column c of row i is stored at circular position c % WC, the RHS
+// columns at positions WC … WC+NRHS-1.
+// ------------------------------------------------------------------------------------------------
+template <int WS>
+__device__ __forceinline__ void assemble_matrix(double* __restrict__ Cg, const double* __restrict__ jv,
+                                                const double* __restrict__ th, const double* __restrict__ dinv,
+                                                double tol, int lane) {
+  // zero fill (scratch is padded to an even number of doubles and 16-byte aligned)
+  double2* C2 = reinterpret_cast<double2*>(Cg);
+  for (int i = lane; i < (NRED * WS + 1) / 2; i += 32) C2[i] = make_double2(0.0, 0.0);
+  __syncwarp();
+  for (int d = lane; d < ND; d += 32) {
+    const unsigned rc = (unsigned)D_RC[d];
+    const int tp = D_TP[d];
+    const int t1 = D_TP[d + 1] & 0x7fffffff;
+    double acc = (tp < 0) ? tol : 0.0;  // sign bit of D_TP marks a diagonal dest
+    for (int t = tp & 0x7fffffff; t < t1; ++t) {
+      double v = T_COEF[t] * opval(T_A[t], jv, th);
+      const int k = T_K[t];
+      if (k >= 0) v *= dinv[k] * opval(T_B[t], jv, th);
+      acc += v;
+    }
+    Cg[(rc >> 16) * WS + (rc & 0xffff)] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded LU with partial pivoting on a sliding window held in shared memory, forward substitution
+// folded into the elimination (RHS columns ride along as extra window columns), then back substitution
+// streaming the U rows back from the scratch.  One warp.
+//
+//   W   : shared, WR slots × WS doubles.  Slots are never swapped: the pivot's slot is retired and
+//         re-used by the row entering the window, which is what makes pivoting free of data movement.
+//   Cg  : global scratch, NRED × WS; holds the assembled rows on entry, the U rows (with the
+//         reciprocal pivot on the diagonal position) on exit.
+//   sol : shared, NRHS × NRED (sol[q*NRED + c]) in the permuted ordering.
+// Lanes own window COLUMNS (positions lane, lane+32, …); rows with a zero multiplier are skipped
+// warp-uniformly, so sparsity inside the band costs nothing.
+// Returns 0, or 1 if a pivot is zero / non-finite (the reference's `:failed` retcode branch,
+// src/solver.jl:84-88).
+// ------------------------------------------------------------------------------------------------
+template <int NRHS, int WS>
+__device__ int band_solve(double* __restrict__ W, double* __restrict__ Cg, double* __restrict__ sol, int lane) {
+  constexpr int CPL = (WC + NRHS + 31) / 32;  // window positions per lane (matrix + rhs)
+  constexpr int CPW = (WC + 31) / 32;         // matrix positions per lane
+  constexpr int RPL = (WR + 31) / 32;         // row slots per lane (pivot search / multipliers)
+  constexpr int WPL = (WS + 31) / 32;         // row copy chunks per lane
+
+  // ---- initial window: rows 0 … WR-1 -----------------------------------------------------------
+  for (int r = 0; r < WR; ++r)
+    for (int q = lane; q < WS; q += 32) W[r * WS + q] = Cg[r * WS + q];
+  int ext[RPL];  // last structurally non-zero column of the row in my slots
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    const int r = lane + 32 * k;
+    ext[k] = (r < WR) ? min(r + KU, NRED - 1) : -1;
+  }
+  __syncwarp();
+
+  int cj = 0;  // j % WC
+  for (int j = 0; j < NRED; ++j) {
+    // prefetch the row that will enter the window at the end of this step
+    const int ienter = j + WR;
+    double pre[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int q = lane + 32 * k;
+      pre[k] = (ienter < NRED && q < WS) ? Cg[ienter * WS + q] : 0.0;
+    }
+
+    // ---- pivot search over column j: max |a| with 12-bit-truncated mantissa, slot in the low byte ----
+    unsigned best = 0;
+    double m[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      const int r = lane + 32 * k;
+      m[k] = (r < WR) ? W[r * WS + cj] : 0.0;
+      if (r < WR) {
+        const unsigned key = ((unsigned)__double2hiint(fabs(m[k])) & 0xffffff00u) | (unsigned)(255 - r);
+        best = max(best, key);
+      }
+    }
+    best = __reduce_max_sync(FULLMASK, best);
+    const int p = 255 - (int)(best & 0xffu);
+    const double piv = W[p * WS + cj];
+    if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1.0e300 * 1.0e300)) return 1;  // zero, NaN or Inf pivot
+    const double rp = 1.0 / piv;
+
+    int extp = ext[0];
+#pragma unroll
+    for (int k = 1; k < RPL; ++k)
+      if ((p >> 5) == k) extp = ext[k];
+    extp = __shfl_sync(FULLMASK, extp, p & 31);
+    const int span = extp - j;
+
+    // ---- my columns of the pivot row ------------------------------------------------------------
+    double u[CPL];
+    bool act[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int q = lane + 32 * k;
+      if (q < WC) {
+        int d = q - cj;
+        if (d < 0) d += WC;
+        act[k] = (d >= 1) && (d <= span);
+      } else {
+        act[k] = (q < WC + NRHS);
+      }
+      u[k] = act[k] ? W[p * WS + q] : 0.0;
+    }
+
+    // ---- retire the pivot row: U row j (reciprocal pivot on the diagonal) -------------------------
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int q = lane + 32 * k;
+      if (q < WS) {
+        double v = W[p * WS + q];
+        if (q == cj) v = rp;
+        Cg[j * WS + q] = v;
+      }
+    }
+
+    // ---- eliminate column j from every other row with a non-zero entry ---------------------------
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      const bool nz = (m[k] != 0.0) && (lane + 32 * k != p);
+      unsigned mask = __ballot_sync(FULLMASK, nz);
+      if (nz) ext[k] = max(ext[k], extp);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double mm = __shfl_sync(FULLMASK, m[k], src) * rp;
+        double* Wr = W + (src + 32 * k) * WS;
+#pragma unroll
+        for (int kk = 0; kk < CPL; ++kk) {
+          if (act[kk]) {
+            const int q = lane + 32 * kk;
+            Wr[q] = fma(-mm, u[kk], Wr[q]);
+          }
+        }
+        if (lane == 0) Wr[cj] = 0.0;
+      }
+    }
+    __syncwarp();
+
+    // ---- the entering row takes the retired slot ---------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int q = lane + 32 * k;
+      if (q < WS) W[p * WS + q] = pre[k];
+    }
+    if (lane == (p & 31)) {
+      const int e = (ienter < NRED) ? min(ienter + KU, NRED - 1) : -1;
+#pragma unroll
+      for (int k = 0; k < RPL; ++k)
+        if ((p >> 5) == k) ext[k] = e;
+    }
+    __syncwarp();
+    cj = (cj + 1 == WC) ? 0 : cj + 1;
+  }
+
+  // ---- back substitution -----------------------------------------------------------------------------
+  __threadfence_block();
+  cj = (NRED - 1) % WC;
+  double cur[CPW], rhs_cur = 0.0, nxt[CPW], rhs_nxt = 0.0;
+#pragma unroll
+  for (int k = 0; k < CPW; ++k) {
+    const int q = lane + 32 * k;
+    cur[k] = (q < WC) ? Cg[(NRED - 1) * WS + q] : 0.0;
+  }
+  if (lane < NRHS) rhs_cur = Cg[(NRED - 1) * WS + WC + lane];
+  for (int j = NRED - 1; j >= 0; --j) {
+    if (j > 0) {
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int q = lane + 32 * k;
+        nxt[k] = (q < WC) ? Cg[(j - 1) * WS + q] : 0.0;
+      }
+      if (lane < NRHS) rhs_nxt = Cg[(j - 1) * WS + WC + lane];
+    }
+    const int span = min(WC - 1, NRED - 1 - j);
+    double acc[NRHS];
+#pragma unroll
+    for (int q = 0; q < NRHS; ++q) acc[q] = 0.0;
+    double rdiag = 0.0;
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) {
+      const int q = lane + 32 * k;
+      if (q < WC) {
+        int d = q - cj;
+        if (d < 0) d += WC;
+        if (d == 0) rdiag = cur[k];
+        if (d >= 1 && d <= span) {
+#pragma unroll
+          for (int rq = 0; rq < NRHS; ++rq) acc[rq] = fma(cur[k], sol[rq * NRED + j + d], acc[rq]);
+        }
+      }
+    }
+    rdiag = __shfl_sync(FULLMASK, rdiag, cj & 31);
+    double mine = 0.0;
+#pragma unroll
+    for (int rq = 0; rq < NRHS; ++rq) {
+      const double tot = warp_sum(acc[rq]);
+      if (lane == rq) mine = tot;
+    }
+    if (lane < NRHS) sol[lane * NRED + j] = (rhs_cur - mine) * rdiag;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) cur[k] = nxt[k];
+    rhs_cur = rhs_nxt;
+    cj = (cj == 0) ? WC - 1 : cj - 1;
+  }
+  return 0;
+}
+
+// `fraction_to_the_boundary_linesearch` — src/solver.jl:127-138, literally (τ = 0.995, decay = 0.5).
+__device__ __forceinline__ double ftb_linesearch(const double* __restrict__ v, const double* __restrict__ d,
+                                                 double min_step, int lane) {
+  const double c = 1.0 - 0.995;
+  double alpha = 1.0;
+  for (int it = 0; it < 1200; ++it) {
+    bool viol = false;
+    for (int k = lane; k < NY; k += 32) viol = viol || (v[k] + alpha * d[k] < c * v[k]);  // :129
+    if (!__any_sync(FULLMASK, viol)) return alpha;
+    if (alpha < min_step) break;  // :130 — tested before halving
+    alpha *= 0.5;                 // :134
+  }
+  return __longlong_as_double(0x7ff8000000000000LL);  // NaN (:131)
+}
+
+// ------------------------------------------------------------------------------------------------
+// The solve kernel: persistent warps pull instances from a global queue.
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kernel(const SolveParams p) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* S = smem + (size_t)warp * SOLVE_SMEM_DOUBLES;
+  double* x = S + SOLVE_OFF_X;
+  double* y = S + SOLVE_OFF_Y;
+  double* s = S + SOLVE_OFF_S;
+  double* gh = S + SOLVE_OFF_GH;
+  double* jv = S + SOLVE_OFF_JV;
+  double* dinv = S + SOLVE_OFF_DINV;  // D⁻¹, later δs
+  double* w = S + SOLVE_OFF_W;        // w, later δy
+  double* sol = S + SOLVE_OFF_SOL;    // δx in the permuted ordering
+  double* W = S + SOLVE_OFF_WIN;
+#if THETA_IN_SMEM
+  double* th = S + SOLVE_OFF_TH;
+#endif
+  double* Cg = p.scratch + ((size_t)blockIdx.x * SOLVE_WARPS + warp) * SOLVE_SCRATCH;
+  const double tol = p.tol;
+
+  for (;;) {
+    unsigned long long inst = 0;
+    if (lane == 0) inst = atomicAdd(p.counters, 1ULL);
+    inst = __shfl_sync(FULLMASK, inst, 0);
+    if (inst >= (unsigned long long)p.B) break;
+
+    // ---- load θ and the initial point (src/solver.jl:39-41,64-66) -------------------------------
+#if THETA_IN_SMEM
+    for (int i = lane; i < NT; i += 32) th[i] = p.theta[inst * NT + i];
+#else
+    const double* th = p.theta + inst * NT;
+#endif
+    for (int i = lane; i < NX; i += 32) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+    for (int i = lane; i < NY; i += 32) {
+      y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+      s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+    }
+    __syncwarp();
+
+    double eps = 1.0;                                        // :67
+    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // Inf, :68
+    int status = 0;                                          // :69
+    int outer = 1;                                           // :70
+    int steps = 0;
+    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      int inner = 1;                                         // :72
+      status = 0;                                            // :73
+      while (kkt > eps && inner < p.max_inner) {             // :75
+        // F and the Jacobian entries at the current iterate (:79-80)
+        if (lane == 0) mcp_eval_newton(x, y, th, gh, jv);
+        __syncwarp();
+        double fmax_ = 0.0;
+        for (int i = lane; i < NX; i += 32) fmax_ = nanmax(fmax_, fabs(gh[i]));
+        for (int k = lane; k < NY; k += 32) {
+          const double f2 = gh[NX + k] - s[k];         // H − s        (src/mcp.jl:78)
+          const double f3 = s[k] * y[k] - eps;         // s∘y − ϵ      (src/mcp.jl:79)
+          const double yt = y[k] + tol;                // (3,3) block diag(y) + tol·I  (:81)
+          const double di = 1.0 / (tol + s[k] / yt);   // D⁻¹, D = (2,2) block tol·I + S (Y+tol)⁻¹
+          dinv[k] = di;
+          w[k] = di * (-f2 - f3 / yt);
+          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+        }
+        const double kkt_new = warp_nanmax(fmax_);           // ‖F‖∞ of the pre-step residual (:107)
+        __syncwarp();
+
+        // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
+        assemble_matrix<WS1>(Cg, jv, th, dinv, tol, lane);
+        for (int i = lane; i < NRED; i += 32) {
+          double r = -gh[R_GROW[i]];
+          for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
+          Cg[i * WS1 + WC] = r;
+        }
+        __syncwarp();
+        if (band_solve<1, WS1>(W, Cg, sol, lane)) {          // :84-88
+          status = 1;
+          break;
+        }
+        // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
+        for (int k = lane; k < NY; k += 32) {
+          double hx = 0.0;
+          for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
+          const double dy = w[k] - dinv[k] * hx;
+          const double f3 = s[k] * y[k] - eps;
+          w[k] = dy;
+          dinv[k] = -(f3 + s[k] * dy) / (y[k] + tol);
+        }
+        __syncwarp();
+        const double a_s = ftb_linesearch(s, dinv, p.min_stepsize, lane);  // :93
+        const double a_y = ftb_linesearch(y, w, p.min_stepsize, lane);     // :94
+        if (a_s != a_s || a_y != a_y) {                                    // :96-100
+          status = 1;
+          break;
+        }
+        for (int c = lane; c < NRED; c += 32) x[PERM[c]] += a_s * sol[c];  // :103 (x uses α_s)
+        for (int k = lane; k < NY; k += 32) {
+          s[k] += a_s * dinv[k];                                           // :104
+          y[k] += a_y * w[k];                                              // :105
+        }
+        __syncwarp();
+        kkt = kkt_new;                                                     // :107
+        ++inner;                                                           // :108
+        ++steps;
+      }
+      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
+      ++outer;                                                             // :114
+    }
+    if (outer == p.max_outer) status = 1;                                  // :117-119
+
+    for (int i = lane; i < NX; i += 32) p.x_out[inst * NX + i] = x[i];
+    for (int i = lane; i < NY; i += 32) {
+      p.y_out[inst * NY + i] = y[i];
+      p.s_out[inst * NY + i] = s[i];
+    }
+    if (lane == 0) {
+      p.kkt_out[inst] = kkt;
+      p.eps_out[inst] = eps;
+      p.outer_out[inst] = outer;
+      p.status_out[inst] = status;
+      if (p.steps_out) p.steps_out[inst] = steps;
+      atomicAdd(p.counters + 1, (unsigned long long)steps);
+      if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sensitivity kernel: ∂z/∂θ = (−∇F_z)⁻¹ ∇F_θ at the returned point, no tol·I (src/AutoDiff.jl:18-40),
+// through the same condensation with D = S Y⁻¹, NRHS_SENS right-hand sides per factorisation pass.
+// ------------------------------------------------------------------------------------------------
+#if HAS_JT
+extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel(const SensParams p) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* S = smem + (size_t)warp * SENS_SMEM_DOUBLES;
+  double* x = S + SENS_OFF_X;
+  double* y = S + SENS_OFF_Y;
+  double* s = S + SENS_OFF_S;
+  double* jv = S + SENS_OFF_JV;
+  double* jtv = S + SENS_OFF_JTV;
+  double* dinv = S + SENS_OFF_DINV;
+  double* wq = S + SENS_OFF_WQ;    // [NRHS_SENS][NY]
+  double* sol = S + SENS_OFF_SOL;  // [NRHS_SENS][NRED]
+  double* W = S + SENS_OFF_WIN;
+#if THETA_IN_SMEM
+  double* th = S + SENS_OFF_TH;
+#endif
+  double* Cg = p.scratch + ((size_t)blockIdx.x * SENS_WARPS + warp) * SENS_SCRATCH;
+  constexpr int NZ = NX + 2 * NY;
+
+  for (;;) {
+    unsigned long long inst = 0;
+    if (lane == 0) inst = atomicAdd(p.counters, 1ULL);
+    inst = __shfl_sync(FULLMASK, inst, 0);
+    if (inst >= (unsigned long long)p.B) break;
+#if THETA_IN_SMEM
+    for (int i = lane; i < NT; i += 32) th[i] = p.theta[inst * NT + i];
+#else
+    const double* th = p.theta + inst * NT;
+#endif
+    for (int i = lane; i < NX; i += 32) x[i] = p.x[inst * NX + i];
+    for (int i = lane; i < NY; i += 32) {
+      y[i] = p.y[inst * NY + i];
+      s[i] = p.s[inst * NY + i];
+    }
+    __syncwarp();
+    if (lane == 0) mcp_eval_sens(x, y, th, jv, jtv);
+    __syncwarp();
+    for (int k = lane; k < NY; k += 32) dinv[k] = y[k] / s[k];  // D⁻¹ with D = s/y (tol = 0)
+    if (p.z_p)
+      for (int i = lane; i < NZ * p.P; i += 32) p.z_p[inst * NZ * p.P + i] = 0.0;
+    __syncwarp();
+    int bad = 0;
+    for (int q0 = 0; q0 < NT; q0 += NRHS_SENS) {
+      const int nq = min(NRHS_SENS, NT - q0);
+      for (int i = lane; i < NRHS_SENS * NY; i += 32) wq[i] = 0.0;
+      assemble_matrix<WSS>(Cg, jv, th, dinv, 0.0, lane);
+      __syncwarp();
+      // right-hand sides r = −∇F_θ[:, q]:  G rows go to the reduced rhs, H rows to w = D⁻¹ r₂
+      for (int rq = 0; rq < nq; ++rq) {
+        const int q = q0 + rq;
+        for (int e = Q_PTR[q] + lane; e < Q_PTR[q + 1]; e += 32) {
+          const double v = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
+          const int row = Q_ROW[e];
+          if (row < NX) Cg[IPERM[row] * WSS + WC + rq] = v;
+          else wq[rq * NY + (row - NX)] = dinv[row - NX] * v;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < NRED; i += 32) {
+        for (int rq = 0; rq < nq; ++rq) {
+          double r = Cg[i * WSS + WC + rq];
+          for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
+            r -= R_COEF[e] * opval(R_CODE[e], jv, th) * wq[rq * NY + R_K[e]];
+          Cg[i * WSS + WC + rq] = r;
+        }
+      }
+      __syncwarp();
+      if (band_solve<NRHS_SENS, WSS>(W, Cg, sol, lane)) {
+        bad = 1;
+        break;
+      }
+      // recover the y and s rows:  Z_y = w − D⁻¹ H_x Z_x ,  Z_s = −s Z_y / y
+      for (int rq = 0; rq < nq; ++rq) {
+        const int q = q0 + rq;
+        const double* so = sol + rq * NRED;
+        double tb = 0.0;
+        for (int c = lane; c < NRED; c += 32) {
+          const double zx = so[c];
+          const int row = PERM[c];
+          if (p.dzdtheta) p.dzdtheta[(inst * NT + q) * NZ + row] = zx;
+          if (p.zbar) tb += p.zbar[inst * NZ + row] * zx;
+          if (p.z_p)
+            for (int pp = 0; pp < p.P; ++pp)
+              p.z_p[(inst * p.P + pp) * NZ + row] += zx * p.theta_p[(inst * p.P + pp) * NT + q];
+        }
+        for (int k = lane; k < NY; k += 32) {
+          double hx = 0.0;
+          for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * so[H_COL[e]];
+          const double zy = wq[rq * NY + k] - dinv[k] * hx;
+          const double zs = -s[k] * zy / y[k];
+          if (p.dzdtheta) {
+            p.dzdtheta[(inst * NT + q) * NZ + NX + k] = zy;
+            p.dzdtheta[(inst * NT + q) * NZ + NX + NY + k] = zs;
+          }
+          if (p.zbar) tb += p.zbar[inst * NZ + NX + k] * zy + p.zbar[inst * NZ + NX + NY + k] * zs;
+          if (p.z_p)
+            for (int pp = 0; pp < p.P; ++pp) {
+              const double tp = p.theta_p[(inst * p.P + pp) * NT + q];
+              p.z_p[(inst * p.P + pp) * NZ + NX + k] += zy * tp;
+              p.z_p[(inst * p.P + pp) * NZ + NX + NY + k] += zs * tp;
+            }
+        }
+        if (p.thetabar) {
+          tb = warp_sum(tb);
+          if (lane == 0) p.thetabar[inst * NT + q] = tb;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && p.status_out) p.status_out[inst] = bad;
+    __syncwarp();
+  }
+}
+#endif  // HAS_JT

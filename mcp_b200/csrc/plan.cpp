@@ -1,0 +1,603 @@
+// plan.cpp — see plan.h.
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <queue>
+#include <set>
+#include <sstream>
+
+namespace mcpb200 {
+namespace {
+
+constexpr int kMaxWindowRows = 256;     // pivot key keeps the slot in 8 bits (kernel_template.cuh)
+constexpr int kMaxSensRhs = 16;
+constexpr int kSmemBudget = 227 * 1024; // bytes per CTA on sm_100a
+constexpr int kThetaSmemMax = 512;      // θ longer than this is read from global memory in place
+
+bool is_binary(int op) { return op >= MCPB200_OP_ADD && op <= MCPB200_OP_DIV; }
+bool is_leaf(int op) { return op >= MCPB200_OP_CONST && op <= MCPB200_OP_THETA; }
+
+struct Entry {  // one non-zero of a sparse block
+  int row, col, idx;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Reverse Cuthill–McKee on a symmetric adjacency structure, several start nodes per component.
+// ---------------------------------------------------------------------------------------------------
+std::vector<int> cuthill_mckee_from(const std::vector<std::vector<int>>& adj, int start, std::vector<char>& seen) {
+  std::vector<int> order;
+  std::queue<int> q;
+  q.push(start);
+  seen[start] = 1;
+  while (!q.empty()) {
+    int v = q.front();
+    q.pop();
+    order.push_back(v);
+    std::vector<int> nb;
+    for (int u : adj[v])
+      if (!seen[u]) {
+        seen[u] = 1;
+        nb.push_back(u);
+      }
+    std::sort(nb.begin(), nb.end(), [&](int a, int b) {
+      return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b;
+    });
+    for (int u : nb) q.push(u);
+  }
+  return order;
+}
+
+void bandwidth_of(const std::vector<std::pair<int, int>>& pattern, const std::vector<int>& iperm, int& kl, int& ku) {
+  kl = ku = 0;
+  for (auto& rc : pattern) {
+    int d = iperm[rc.first] - iperm[rc.second];
+    if (d > kl) kl = d;
+    if (-d > ku) ku = -d;
+  }
+}
+
+double window_cost(int kl, int ku, int n) {
+  double r = std::min(kl + 1, n), c = std::min(kl + ku + 1, n);
+  return r * c;
+}
+
+// far node of a BFS from `s` (last level, min degree): pseudo-peripheral node heuristic
+int far_node(const std::vector<std::vector<int>>& adj, int s, const std::vector<int>& comp_id, int comp) {
+  std::vector<int> dist(adj.size(), -1);
+  std::queue<int> q;
+  q.push(s);
+  dist[s] = 0;
+  int best = s;
+  while (!q.empty()) {
+    int v = q.front();
+    q.pop();
+    if (dist[v] > dist[best] || (dist[v] == dist[best] && adj[v].size() < adj[best].size())) best = v;
+    for (int u : adj[v])
+      if (dist[u] < 0 && comp_id[u] == comp) {
+        dist[u] = dist[v] + 1;
+        q.push(u);
+      }
+  }
+  return best;
+}
+
+std::vector<int> rcm_ordering(int n, const std::vector<std::pair<int, int>>& pattern) {
+  std::vector<std::vector<int>> adj(n);
+  {
+    std::set<std::pair<int, int>> seen;
+    for (auto& rc : pattern) {
+      if (rc.first == rc.second) continue;
+      int a = std::min(rc.first, rc.second), b = std::max(rc.first, rc.second);
+      if (seen.insert({a, b}).second) {
+        adj[a].push_back(b);
+        adj[b].push_back(a);
+      }
+    }
+  }
+  // components
+  std::vector<int> comp_id(n, -1);
+  int ncomp = 0;
+  for (int v = 0; v < n; ++v) {
+    if (comp_id[v] >= 0) continue;
+    std::queue<int> q;
+    q.push(v);
+    comp_id[v] = ncomp;
+    while (!q.empty()) {
+      int w = q.front();
+      q.pop();
+      for (int u : adj[w])
+        if (comp_id[u] < 0) {
+          comp_id[u] = ncomp;
+          q.push(u);
+        }
+    }
+    ++ncomp;
+  }
+  std::vector<int> perm;
+  perm.reserve(n);
+  for (int c = 0; c < ncomp; ++c) {
+    std::vector<int> nodes;
+    for (int v = 0; v < n; ++v)
+      if (comp_id[v] == c) nodes.push_back(v);
+    // candidate starts: pseudo-peripheral nodes reached from the min-degree nodes
+    std::sort(nodes.begin(), nodes.end(), [&](int a, int b) {
+      return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b;
+    });
+    std::set<int> starts;
+    for (size_t i = 0; i < nodes.size() && starts.size() < 12; ++i) {
+      int s = nodes[i];
+      for (int it = 0; it < 3; ++it) s = far_node(adj, s, comp_id, c);
+      starts.insert(s);
+      starts.insert(nodes[i]);
+    }
+    std::vector<int> best_order;
+    double best_cost = 1e300;
+    std::vector<std::pair<int, int>> sub;
+    for (auto& rc : pattern)
+      if (comp_id[rc.first] == c && comp_id[rc.second] == c) sub.push_back(rc);
+    for (int s : starts) {
+      std::vector<char> seen(n, 0);
+      std::vector<int> order = cuthill_mckee_from(adj, s, seen);
+      std::reverse(order.begin(), order.end());
+      std::vector<int> ip(n, 0);
+      for (size_t i = 0; i < order.size(); ++i) ip[order[i]] = (int)i;
+      int kl, ku;
+      bandwidth_of(sub, ip, kl, ku);
+      double cost = window_cost(kl, ku, (int)order.size());
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_order = order;
+      }
+    }
+    perm.insert(perm.end(), best_order.begin(), best_order.end());
+  }
+  return perm;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// source emission helpers
+// ---------------------------------------------------------------------------------------------------
+std::string dlit(double v) {
+  char buf[64];
+  if (std::isnan(v)) return "__longlong_as_double(0x7ff8000000000000LL)";
+  if (std::isinf(v)) return v > 0 ? "__longlong_as_double(0x7ff0000000000000LL)" : "__longlong_as_double(0xfff0000000000000LL)";
+  snprintf(buf, sizeof buf, "%.17g", v);
+  std::string s(buf);
+  if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+  return s;
+}
+
+template <class T>
+void emit_table(std::ostringstream& os, const char* type, const char* name, const std::vector<T>& v, bool is_double = false) {
+  os << "__device__ const " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+  if (v.empty()) os << "0";
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (i) os << ",";
+    if (i % 16 == 15) os << "\n";
+    if (is_double) os << dlit((double)v[i]);
+    else os << (long long)v[i];
+  }
+  os << "};\n";
+}
+
+struct Emitter {
+  const Plan& P;
+  explicit Emitter(const Plan& p) : P(p) {}
+
+  std::string operand(int n) const {
+    const int op = P.op[n];
+    char buf[64];
+    switch (op) {
+      case MCPB200_OP_CONST: return "(" + dlit(P.consts[P.a[n]]) + ")";
+      case MCPB200_OP_X: snprintf(buf, sizeof buf, "x[%d]", P.a[n]); return buf;
+      case MCPB200_OP_Y: snprintf(buf, sizeof buf, "y[%d]", P.a[n]); return buf;
+      case MCPB200_OP_THETA: snprintf(buf, sizeof buf, "th[%d]", P.a[n]); return buf;
+      default: snprintf(buf, sizeof buf, "v%d", n); return buf;
+    }
+  }
+
+  // emits `const double vN = …;` for every non-leaf node the roots need
+  void body(std::ostringstream& os, const std::vector<int32_t>& roots) const {
+    std::vector<char> need(P.op.size(), 0);
+    std::vector<int> stack(roots.begin(), roots.end());
+    while (!stack.empty()) {
+      int n = stack.back();
+      stack.pop_back();
+      if (need[n]) continue;
+      need[n] = 1;
+      const int op = P.op[n];
+      if (is_binary(op)) {
+        stack.push_back(P.a[n]);
+        stack.push_back(P.b[n]);
+      } else if (!is_leaf(op)) {
+        stack.push_back(P.a[n]);
+      }
+    }
+    for (size_t n = 0; n < P.op.size(); ++n) {
+      if (!need[n] || is_leaf(P.op[n])) continue;
+      const std::string A = operand(P.a[n]);
+      os << "  const double v" << n << " = ";
+      switch (P.op[n]) {
+        case MCPB200_OP_ADD: os << A << " + " << operand(P.b[n]); break;
+        case MCPB200_OP_SUB: os << A << " - " << operand(P.b[n]); break;
+        case MCPB200_OP_MUL: os << A << " * " << operand(P.b[n]); break;
+        case MCPB200_OP_DIV: os << A << " / " << operand(P.b[n]); break;
+        case MCPB200_OP_NEG: os << "-" << A; break;
+        case MCPB200_OP_SQRT: os << "sqrt(" << A << ")"; break;
+        case MCPB200_OP_EXP: os << "exp(" << A << ")"; break;
+        case MCPB200_OP_LOG: os << "log(" << A << ")"; break;
+        case MCPB200_OP_SIN: os << "sin(" << A << ")"; break;
+        case MCPB200_OP_COS: os << "cos(" << A << ")"; break;
+        case MCPB200_OP_POWI: os << "mcp_powi(" << A << ", " << P.b[n] << ")"; break;
+        default: os << "0.0"; break;
+      }
+      os << ";\n";
+    }
+  }
+};
+
+Operand classify(const Plan& P, int node, std::map<int, int>& slot_of_node, std::vector<int32_t>& slot_nodes) {
+  const int op = P.op[node];
+  if (op == MCPB200_OP_CONST) return {P.consts[P.a[node]], -1};
+  if (op == MCPB200_OP_THETA) return {1.0, -2 - P.a[node]};
+  if (op == MCPB200_OP_NEG && P.op[P.a[node]] == MCPB200_OP_THETA) return {-1.0, -2 - P.a[P.a[node]]};
+  if (op == MCPB200_OP_MUL) {
+    const int a = P.a[node], b = P.b[node];
+    if (P.op[a] == MCPB200_OP_CONST && P.op[b] == MCPB200_OP_THETA) return {P.consts[P.a[a]], -2 - P.a[b]};
+    if (P.op[b] == MCPB200_OP_CONST && P.op[a] == MCPB200_OP_THETA) return {P.consts[P.a[b]], -2 - P.a[a]};
+  }
+  auto it = slot_of_node.find(node);
+  if (it == slot_of_node.end()) {
+    it = slot_of_node.emplace(node, (int)slot_nodes.size()).first;
+    slot_nodes.push_back(node);
+  }
+  return {1.0, it->second};
+}
+
+int odd_at_least(int v) { return (v & 1) ? v : v + 1; }
+
+}  // namespace
+
+// ===================================================================================================
+int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template, Plan& P) {
+  auto fail = [&](int code, const std::string& msg) {
+    P.error = msg;
+    return code;
+  };
+  // ---- copy + validate the IR ----------------------------------------------------------------------
+  if (d.nx <= 0 || d.ny < 0 || d.ntheta < 0 || d.n_nodes <= 0 || d.jz_nnz < 0)
+    return fail(MCPB200_ERR_INVALID_ARGUMENT, "invalid problem dimensions (need nx > 0, ny >= 0, ntheta >= 0)");
+  if (!d.op || !d.a || !d.b || !d.gh_nodes || (d.jz_nnz > 0 && (!d.jz_rows || !d.jz_cols || !d.jz_nodes)))
+    return fail(MCPB200_ERR_INVALID_ARGUMENT, "null IR array");
+  P.nx = d.nx;
+  P.ny = d.ny;
+  P.nt = d.ntheta;
+  P.op.assign(d.op, d.op + d.n_nodes);
+  P.a.assign(d.a, d.a + d.n_nodes);
+  P.b.assign(d.b, d.b + d.n_nodes);
+  P.consts.assign(d.consts, d.consts + std::max(d.n_consts, 0));
+  P.gh_nodes.assign(d.gh_nodes, d.gh_nodes + d.nx + d.ny);
+  P.jz_rows.assign(d.jz_rows, d.jz_rows + d.jz_nnz);
+  P.jz_cols.assign(d.jz_cols, d.jz_cols + d.jz_nnz);
+  P.jz_nodes.assign(d.jz_nodes, d.jz_nodes + d.jz_nnz);
+  P.has_jt = d.jt_nnz >= 0;
+  if (P.has_jt && d.jt_nnz > 0) {
+    if (!d.jt_rows || !d.jt_cols || !d.jt_nodes) return fail(MCPB200_ERR_INVALID_ARGUMENT, "null θ-Jacobian array");
+    P.jt_rows.assign(d.jt_rows, d.jt_rows + d.jt_nnz);
+    P.jt_cols.assign(d.jt_cols, d.jt_cols + d.jt_nnz);
+    P.jt_nodes.assign(d.jt_nodes, d.jt_nodes + d.jt_nnz);
+  }
+  const int nx = P.nx, ny = P.ny, nt = P.nt, nn = d.n_nodes;
+  for (int n = 0; n < nn; ++n) {
+    const int op = P.op[n], a = P.a[n], b = P.b[n];
+    bool ok = true;
+    switch (op) {
+      case MCPB200_OP_CONST: ok = a >= 0 && a < d.n_consts; break;
+      case MCPB200_OP_X: ok = a >= 0 && a < nx; break;
+      case MCPB200_OP_Y: ok = a >= 0 && a < ny; break;
+      case MCPB200_OP_THETA: ok = a >= 0 && a < nt; break;
+      case MCPB200_OP_ADD: case MCPB200_OP_SUB: case MCPB200_OP_MUL: case MCPB200_OP_DIV:
+        ok = a >= 0 && a < n && b >= 0 && b < n; break;
+      case MCPB200_OP_NEG: case MCPB200_OP_SQRT: case MCPB200_OP_EXP: case MCPB200_OP_LOG:
+      case MCPB200_OP_SIN: case MCPB200_OP_COS: case MCPB200_OP_POWI:
+        ok = a >= 0 && a < n; break;
+      default: ok = false;
+    }
+    if (!ok) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "malformed IR node %d (op %d, a %d, b %d): operands must precede users", n, op, a, b);
+      return fail(MCPB200_ERR_INVALID_ARGUMENT, buf);
+    }
+  }
+  auto node_ok = [&](int v) { return v >= 0 && v < nn; };
+  for (int v : P.gh_nodes) if (!node_ok(v)) return fail(MCPB200_ERR_INVALID_ARGUMENT, "gh_nodes out of range");
+  for (size_t k = 0; k < P.jz_nodes.size(); ++k)
+    if (!node_ok(P.jz_nodes[k]) || P.jz_rows[k] < 0 || P.jz_rows[k] >= nx + ny || P.jz_cols[k] < 0 || P.jz_cols[k] >= nx + ny)
+      return fail(MCPB200_ERR_INVALID_ARGUMENT, "Jacobian entry out of range");
+  for (size_t k = 0; k < P.jt_nodes.size(); ++k)
+    if (!node_ok(P.jt_nodes[k]) || P.jt_rows[k] < 0 || P.jt_rows[k] >= nx + ny || P.jt_cols[k] < 0 || P.jt_cols[k] >= nt)
+      return fail(MCPB200_ERR_INVALID_ARGUMENT, "θ-Jacobian entry out of range");
+
+  // ---- classify Jacobian entries --------------------------------------------------------------------
+  {
+    std::map<int, int> slots;
+    P.jz_opnd.resize(P.jz_nodes.size());
+    for (size_t k = 0; k < P.jz_nodes.size(); ++k) {
+      P.jz_opnd[k] = classify(P, P.jz_nodes[k], slots, P.jv_nodes);
+      if (P.jz_opnd[k].code == -1) ++P.n_const_entries;
+    }
+    std::map<int, int> tslots;
+    P.jt_opnd.resize(P.jt_nodes.size());
+    for (size_t k = 0; k < P.jt_nodes.size(); ++k) P.jt_opnd[k] = classify(P, P.jt_nodes[k], tslots, P.jtv_nodes);
+  }
+
+  // ---- blocks of the Jacobian -----------------------------------------------------------------------
+  std::vector<Entry> Gx, Gy, Hx;
+  for (size_t k = 0; k < P.jz_nodes.size(); ++k) {
+    const int r = P.jz_rows[k], c = P.jz_cols[k];
+    if (r < nx && c < nx) Gx.push_back({r, c, (int)k});
+    else if (r < nx) Gy.push_back({r, c - nx, (int)k});
+    else if (c < nx) Hx.push_back({r - nx, c, (int)k});
+    else
+      return fail(MCPB200_ERR_UNSUPPORTED,
+                  "H depends on y (∇_y H ≠ 0): only the condensed mode (∇_y H ≡ 0, true for every reference "
+                  "config) is implemented in this round");
+  }
+  const int N = nx;
+  P.N = N;
+
+  // ---- structure of C = G_x + tol·I − G_y D⁻¹ H_x ------------------------------------------------------
+  std::vector<std::vector<Entry>> gy_by_k(ny), hx_by_k(ny);
+  for (auto& e : Gy) gy_by_k[e.col].push_back(e);
+  for (auto& e : Hx) hx_by_k[e.row].push_back(e);
+  struct Term {
+    double coef;
+    int a, b, k;
+  };
+  std::map<std::pair<int, int>, std::vector<Term>> dest;  // (old row, old col) → terms
+  for (int i = 0; i < N; ++i) dest[{i, i}];               // diagonal always present (tol·I)
+  for (auto& e : Gx) {
+    const Operand& o = P.jz_opnd[e.idx];
+    dest[{e.row, e.col}].push_back({o.coef, o.code, -1, -1});
+  }
+  for (int k = 0; k < ny; ++k)
+    for (auto& g : gy_by_k[k])
+      for (auto& h : hx_by_k[k]) {
+        const Operand& og = P.jz_opnd[g.idx];
+        const Operand& oh = P.jz_opnd[h.idx];
+        dest[{g.row, h.col}].push_back({-og.coef * oh.coef, og.code, oh.code, k});
+      }
+  std::vector<std::pair<int, int>> pattern;
+  pattern.reserve(dest.size());
+  for (auto& kv : dest) pattern.push_back(kv.first);
+
+  // ---- ordering --------------------------------------------------------------------------------------
+  {
+    std::vector<int> ident(N);
+    std::iota(ident.begin(), ident.end(), 0);
+    int kl0, ku0;
+    bandwidth_of(pattern, ident, kl0, ku0);
+    std::vector<int> perm = rcm_ordering(N, pattern);
+    std::vector<int> ip(N);
+    for (int i = 0; i < N; ++i) ip[perm[i]] = i;
+    int kl1, ku1;
+    bandwidth_of(pattern, ip, kl1, ku1);
+    if (window_cost(kl1, ku1, N) < window_cost(kl0, ku0, N)) {
+      P.perm = perm;
+      P.iperm = ip;
+      P.kl = kl1;
+      P.ku = ku1;
+    } else {
+      P.perm = ident;
+      P.iperm = ident;
+      P.kl = kl0;
+      P.ku = ku0;
+    }
+  }
+  P.WC = std::min(P.kl + P.ku + 1, N);
+  P.R = std::min(P.kl + 1, N);
+  if (P.R > kMaxWindowRows) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "condensed system needs %d window rows (bandwidth kl=%d) > %d supported by the "
+             "shared-memory window kernel", P.R, P.kl, kMaxWindowRows);
+    return fail(MCPB200_ERR_UNSUPPORTED, buf);
+  }
+  if (N >= 65536 || P.WC >= 65536) return fail(MCPB200_ERR_UNSUPPORTED, "reduced dimension ≥ 65536");
+  P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
+  P.WS1 = odd_at_least(P.WC + 1);
+  P.WSS = odd_at_least(P.WC + P.nrhs_sens);
+
+  // ---- assembly tables (new ordering) -------------------------------------------------------------------
+  {
+    struct D {
+      int row, col;
+      const std::vector<Term>* terms;
+    };
+    std::vector<D> ds;
+    for (auto& kv : dest) ds.push_back({P.iperm[kv.first.first], P.iperm[kv.first.second], &kv.second});
+    std::sort(ds.begin(), ds.end(), [](const D& a, const D& b) { return a.row != b.row ? a.row < b.row : a.col < b.col; });
+    P.d_tptr.push_back(0);
+    for (auto& dd : ds) {
+      P.d_row.push_back(dd.row);
+      P.d_cpos.push_back(dd.col % P.WC);
+      P.d_diag.push_back(dd.row == dd.col);
+      for (auto& t : *dd.terms) {
+        P.t_coef.push_back(t.coef);
+        P.t_a.push_back(t.a);
+        P.t_b.push_back(t.b);
+        P.t_k.push_back(t.k);
+      }
+      P.d_tptr.push_back((int)P.t_coef.size());
+    }
+    // rhs rows
+    std::vector<std::vector<Entry>> gy_by_row(nx);
+    for (auto& e : Gy) gy_by_row[e.row].push_back(e);
+    P.r_ptr.push_back(0);
+    for (int i = 0; i < N; ++i) {
+      const int old = P.perm[i];
+      P.r_grow.push_back(old);
+      for (auto& e : gy_by_row[old]) {
+        P.r_coef.push_back(P.jz_opnd[e.idx].coef);
+        P.r_code.push_back(P.jz_opnd[e.idx].code);
+        P.r_k.push_back(e.col);
+      }
+      P.r_ptr.push_back((int)P.r_coef.size());
+    }
+    P.h_ptr.push_back(0);
+    for (int k = 0; k < ny; ++k) {
+      for (auto& e : hx_by_k[k]) {
+        P.h_coef.push_back(P.jz_opnd[e.idx].coef);
+        P.h_code.push_back(P.jz_opnd[e.idx].code);
+        P.h_col.push_back(P.iperm[e.col]);
+      }
+      P.h_ptr.push_back((int)P.h_coef.size());
+    }
+    // θ-Jacobian by column
+    std::vector<std::vector<int>> by_q(std::max(nt, 1));
+    for (size_t k = 0; k < P.jt_nodes.size(); ++k) by_q[P.jt_cols[k]].push_back((int)k);
+    P.q_ptr.push_back(0);
+    for (int q = 0; q < nt; ++q) {
+      for (int k : by_q[q]) {
+        P.q_row.push_back(P.jt_rows[k]);
+        P.q_code.push_back(P.jt_opnd[k].code);
+        P.q_coef.push_back(P.jt_opnd[k].coef);
+      }
+      P.q_ptr.push_back((int)P.q_row.size());
+    }
+  }
+
+  // ---- shared-memory layout and launch configuration ---------------------------------------------------
+  P.theta_in_smem = nt <= kThetaSmemMax ? 1 : 0;
+  const int njv = (int)P.jv_nodes.size(), njtv = (int)P.jtv_nodes.size();
+  std::ostringstream lay;
+  auto even = [](int64_t v) { return (v + 1) & ~int64_t(1); };
+  int64_t off = 0;
+  auto place = [&](const char* name, int64_t n) {
+    lay << "#define " << name << " " << off << "\n";
+    off = even(off + n);
+  };
+  place("SOLVE_OFF_X", nx);
+  place("SOLVE_OFF_Y", ny);
+  place("SOLVE_OFF_S", ny);
+  place("SOLVE_OFF_GH", nx + ny);
+  place("SOLVE_OFF_JV", njv);
+  place("SOLVE_OFF_DINV", ny);
+  place("SOLVE_OFF_W", ny);
+  place("SOLVE_OFF_SOL", N);
+  if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
+  place("SOLVE_OFF_WIN", (int64_t)P.R * P.WS1);
+  const int64_t solve_doubles = off;
+  off = 0;
+  place("SENS_OFF_X", nx);
+  place("SENS_OFF_Y", ny);
+  place("SENS_OFF_S", ny);
+  place("SENS_OFF_JV", njv);
+  place("SENS_OFF_JTV", njtv);
+  place("SENS_OFF_DINV", ny);
+  place("SENS_OFF_WQ", (int64_t)P.nrhs_sens * ny);
+  place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
+  if (P.theta_in_smem) place("SENS_OFF_TH", nt);
+  place("SENS_OFF_WIN", (int64_t)P.R * P.WSS);
+  const int64_t sens_doubles = off;
+  auto warps_for = [&](int64_t doubles) {
+    int64_t w = kSmemBudget / (doubles * 8);
+    return (int)std::max<int64_t>(0, std::min<int64_t>(w, 16));
+  };
+  P.ipc_solve = warps_for(solve_doubles);
+  P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
+  if (P.ipc_solve < 1 || P.ipc_sens < 1) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "per-instance working set (%lld bytes) exceeds the %d-byte shared memory of one SM",
+             (long long)(std::max(solve_doubles, sens_doubles) * 8), kSmemBudget);
+    return fail(MCPB200_ERR_UNSUPPORTED, buf);
+  }
+  P.smem_solve = solve_doubles * 8 * P.ipc_solve;
+  P.smem_sens = sens_doubles * 8 * P.ipc_sens;
+  P.scratch_doubles_solve = even((int64_t)N * P.WS1) + 2;
+  P.scratch_doubles_sens = even((int64_t)N * P.WSS) + 2;
+  // banded LU with partial pivoting + forward/back substitution, dense-in-band count
+  {
+    const double kl = P.kl, kuu = std::min(P.kl + P.ku, N - 1);
+    P.flops_band = 2.0 * N * kl * kuu + 2.0 * N * kl + 2.0 * N * kuu;
+  }
+
+  // ---- source ----------------------------------------------------------------------------------------------
+  std::ostringstream os;
+  os << "// generated by libmcpb200 (plan.cpp) — do not edit\n";
+  os << "#define NX " << nx << "\n#define NY " << ny << "\n#define NT " << nt << "\n#define NRED " << N << "\n";
+  os << "#define KL " << P.kl << "\n#define KU " << P.ku << "\n#define WC " << P.WC << "\n#define WR " << P.R << "\n";
+  os << "#define WS1 " << P.WS1 << "\n#define WSS " << P.WSS << "\n#define NRHS_SENS " << P.nrhs_sens << "\n";
+  os << "#define NJV " << njv << "\n#define NJTV " << njtv << "\n#define ND " << P.d_row.size() << "\n";
+  os << "#define THETA_IN_SMEM " << P.theta_in_smem << "\n#define HAS_JT " << (P.has_jt ? 1 : 0) << "\n";
+  os << "#define SOLVE_WARPS " << P.ipc_solve << "\n#define SENS_WARPS " << P.ipc_sens << "\n";
+  os << "#define SOLVE_SMEM_DOUBLES " << solve_doubles << "\n#define SENS_SMEM_DOUBLES " << sens_doubles << "\n";
+  os << "#define SOLVE_SCRATCH " << P.scratch_doubles_solve << "\n#define SENS_SCRATCH " << P.scratch_doubles_sens << "\n";
+  os << lay.str();
+  {
+    std::vector<int32_t> rc(P.d_row.size()), tp(P.d_tptr.size());
+    for (size_t i = 0; i < P.d_row.size(); ++i) rc[i] = (P.d_row[i] << 16) | P.d_cpos[i];
+    for (size_t i = 0; i < P.d_tptr.size(); ++i)
+      tp[i] = P.d_tptr[i] | ((i < P.d_diag.size() && P.d_diag[i]) ? (int32_t)0x80000000 : 0);
+    emit_table(os, "int", "D_RC", rc);
+    emit_table(os, "int", "D_TP", tp);
+  }
+  emit_table(os, "double", "T_COEF", P.t_coef, true);
+  emit_table(os, "int", "T_A", P.t_a);
+  emit_table(os, "int", "T_B", P.t_b);
+  emit_table(os, "int", "T_K", P.t_k);
+  emit_table(os, "int", "R_GROW", P.r_grow);
+  emit_table(os, "int", "R_PTR", P.r_ptr);
+  emit_table(os, "int", "R_CODE", P.r_code);
+  emit_table(os, "int", "R_K", P.r_k);
+  emit_table(os, "double", "R_COEF", P.r_coef, true);
+  emit_table(os, "int", "H_PTR", P.h_ptr);
+  emit_table(os, "int", "H_CODE", P.h_code);
+  emit_table(os, "int", "H_COL", P.h_col);
+  emit_table(os, "double", "H_COEF", P.h_coef, true);
+  emit_table(os, "int", "PERM", P.perm);
+  emit_table(os, "int", "IPERM", P.iperm);
+  if (P.has_jt) {
+    emit_table(os, "int", "Q_PTR", P.q_ptr);
+    emit_table(os, "int", "Q_ROW", P.q_row);
+    emit_table(os, "int", "Q_CODE", P.q_code);
+    emit_table(os, "double", "Q_COEF", P.q_coef, true);
+  }
+  os << "__device__ __forceinline__ double mcp_powi(double a, int n) {\n"
+        "  double r = 1.0; bool neg = n < 0; if (neg) n = -n;\n"
+        "  while (n) { if (n & 1) r *= a; a *= a; n >>= 1; }\n"
+        "  return neg ? 1.0 / r : r;\n}\n";
+  Emitter E(P);
+  // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
+  os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
+  os << "__device__ __noinline__ void mcp_eval_newton(const double* __restrict__ x, const double* __restrict__ y,\n"
+        "    const double* __restrict__ th, double* __restrict__ gh, double* __restrict__ jv) {\n";
+  {
+    std::vector<int32_t> roots(P.gh_nodes);
+    roots.insert(roots.end(), P.jv_nodes.begin(), P.jv_nodes.end());
+    E.body(os, roots);
+    for (int i = 0; i < nx + ny; ++i) os << "  gh[" << i << "] = " << E.operand(P.gh_nodes[i]) << ";\n";
+    for (int i = 0; i < njv; ++i) os << "  jv[" << i << "] = " << E.operand(P.jv_nodes[i]) << ";\n";
+  }
+  os << "}\n";
+  if (P.has_jt) {
+    os << "// computed entries of ∇F_z and ∇F_θ at the solution (src/AutoDiff.jl:27-37)\n";
+    os << "__device__ __noinline__ void mcp_eval_sens(const double* __restrict__ x, const double* __restrict__ y,\n"
+          "    const double* __restrict__ th, double* __restrict__ jv, double* __restrict__ jtv) {\n";
+    std::vector<int32_t> roots(P.jv_nodes);
+    roots.insert(roots.end(), P.jtv_nodes.begin(), P.jtv_nodes.end());
+    E.body(os, roots);
+    for (int i = 0; i < njv; ++i) os << "  jv[" << i << "] = " << E.operand(P.jv_nodes[i]) << ";\n";
+    for (int i = 0; i < njtv; ++i) os << "  jtv[" << i << "] = " << E.operand(P.jtv_nodes[i]) << ";\n";
+    os << "}\n";
+  }
+  os << kernel_template;
+  P.source = os.str();
+  return MCPB200_OK;
+}
+
+}  // namespace mcpb200

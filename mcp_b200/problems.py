@@ -229,9 +229,16 @@ def lane_change_game(horizon: int = 10, height: float = 50.0, num_lanes: int = 2
         compute_sensitivities=compute_sensitivities)
 
 
-def lane_change_thetas(B: int, seed: int = 1, num_lanes=2, lane_width=2.0, height=50.0) -> np.ndarray:
+def lane_change_thetas(B: int, seed: int = 1, num_lanes=2, lane_width=2.0, height=50.0,
+                       moving: bool = False) -> np.ndarray:
     """`generate_random_parameter(::TrajectoryGameBenchmark)` — `trajectory_game_benchmark.jl:62-87`:
-    θ = [p₁ ~ U(road), 0, 0, lane₁; p₂ ~ U(road), 0, 0, lane₂], lanes drawn from the lane centres."""
+    θ = [p₁ ~ U(road), 0, 0, lane₁; p₂ ~ U(road), 0, 0, lane₂], lanes drawn from the lane centres.
+
+    NB the benchmark's zero initial velocity sits exactly on the state bound v_y ≥ 0
+    (`examples/lane_change.jl:49`), so the equality `x₁ = initial_state` and that inequality are linearly
+    dependent: ∇F_z is numerically singular at the solution (cond ≈ 1e16) and sensitivities are not well
+    defined there.  `moving=True` draws v_x ~ U(-1,1), v_y ~ U(0.5,3) instead (the example's own start has
+    v_y = 1, `examples/lane_change.jl:58`) for well-posed sensitivity tests."""
     centers, _, (x0, x1, y0, y1) = road_environment(lane_width, num_lanes, height)
     rng = np.random.default_rng(seed)
     θ = np.zeros((10, B), order="F")
@@ -239,6 +246,9 @@ def lane_change_thetas(B: int, seed: int = 1, num_lanes=2, lane_width=2.0, heigh
         θ[5 * i + 0] = rng.uniform(x0, x1, B)
         θ[5 * i + 1] = rng.uniform(y0, y1, B)
         θ[5 * i + 4] = rng.choice(np.asarray(centers), B)
+        if moving:
+            θ[5 * i + 2] = rng.uniform(-1.0, 1.0, B)
+            θ[5 * i + 3] = rng.uniform(0.5, 3.0, B)
     return θ
 
 

