@@ -1,0 +1,135 @@
+"""CPU tests of the C-ABI boundary: the library loads without a GPU, exports every symbol the header
+declares, compiles problems for sm_100a in COMPILE_ONLY mode, reports API misuse through error codes,
+and refuses — loudly — to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mcp_b200 import capi, problems
+from mcp_b200.mcp import PrimalDualMCP
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "mcpb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcpb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = capi.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/mcpb200.h but not exported"
+    assert sorted(capi.EXPORTS) == syms
+
+
+def test_default_opts_match_reference():
+    """src/solver.jl:42-49."""
+    o = capi.default_opts()
+    assert (o.tol, o.max_inner_iters, o.max_outer_iters) == (1e-4, 20, 50)
+    assert (o.tightening_rate, o.loosening_rate, o.min_stepsize) == (0.1, 0.5, 1e-4)
+
+
+@pytest.mark.parametrize("name", ["readme", "clamp", "lane", "qp12"])
+def test_compile_only_for_sm100a(name):
+    mcp = {"readme": problems.readme_qp, "clamp": lambda: problems.clamp_game().mcp,
+           "lane": lambda: problems.lane_change_game().mcp, "qp12": lambda: problems.random_qp(12, 10)}[name]()
+    h = capi.Handle(mcp.ir, capi.COMPILE_ONLY)
+    info = h.info()
+    assert info["nx"] == mcp.unconstrained_dimension and info["ny"] == mcp.constrained_dimension
+    assert info["n_reduced"] == info["nx"]                     # condensed to the unconstrained block
+    assert 1 <= info["window_rows"] <= 256 and info["window_cols"] <= info["n_reduced"]
+    assert info["smem_bytes_per_cta"] <= 227 * 1024 and info["instances_per_cta"] >= 1
+    src = h.source()
+    assert "mcp_eval_newton" in src and "mcp_solve_kernel" in src
+    if name == "lane":
+        # the fill-reducing ordering must find the stage structure: SURVEY.md App. B measured bandwidth 32
+        # for the stage-major ordering; RCM does better
+        assert info["kl"] <= 20 and info["ku"] <= 20
+        assert info["n_jac_constant"] == 1080 and info["has_sensitivities"] == 1
+    if name == "qp12":
+        assert info["has_sensitivities"] == 0 and info["n_jac_computed"] == 0   # every entry is ±θ_i: read in place
+    h.close()
+
+
+def test_cubin_is_sm100a(tmp_path, monkeypatch):
+    import subprocess
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    h.close()
+    cubins = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(cubins) == 1
+    out = subprocess.run(["cuobjdump", "-lelf", str(tmp_path / cubins[0])], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    # second creation must hit the cache
+    h2 = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    assert h2.info()["cache_hit"] == 1
+    h2.close()
+
+
+def test_invalid_ir_is_rejected():
+    ir = problems.readme_qp().ir
+    bad = type(ir)(**{**ir.__dict__})
+    bad.a = ir.a.copy()
+    k = int(np.nonzero(ir.op == 4)[0][0])     # an ADD node: point its operand at a later node
+    bad.a[k] = len(ir.op) - 1
+    with pytest.raises(capi.MCPB200Error) as e:
+        capi.Handle(bad, capi.COMPILE_ONLY)
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT
+
+
+def test_h_depending_on_y_is_unsupported():
+    mcp = PrimalDualMCP(lambda x, y, θ: x - θ - y, lambda x, y, θ: x + 0.5 * y, unconstrained_dimension=1,
+                        constrained_dimension=1, parameter_dimension=1)
+    with pytest.raises(capi.MCPB200Error) as e:
+        capi.Handle(mcp.ir, capi.COMPILE_ONLY)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point must fail with an error code — never produce numbers."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from mcp_b200 import InteriorPoint, solve
+    with pytest.raises(capi.MCPB200Error) as e:
+        solve(InteriorPoint(), problems.readme_qp(), np.array([-0.5, 0.5]))
+    assert e.value.code == capi.ERR_CUDA
+    # a COMPILE_ONLY handle refuses device work as well
+    h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    out = np.zeros(8)
+    rc = h._lib.mcpb200_solve_batched(h.raw, 1, out.ctypes.data, None, None, None, None, out.ctypes.data,
+                                      out.ctypes.data, out.ctypes.data, out.ctypes.data, out.ctypes.data,
+                                      out.ctypes.data, out.ctypes.data, None)
+    assert rc == capi.ERR_CUDA
+
+
+def test_missing_sensitivities_error_code():
+    """The handle-level analogue of the ArgumentError at src/AutoDiff.jl:19-23."""
+    h = capi.Handle(problems.readme_qp(compute_sensitivities=False).ir, capi.COMPILE_ONLY)
+    z = np.zeros(8)
+    rc = h._lib.mcpb200_sensitivities(h.raw, 1, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data,
+                                      z.ctypes.data, z.ctypes.data, None, None, 0, None, None, None)
+    assert rc == capi.ERR_NO_SENSITIVITIES
+    assert b"Missing sensitivities" in h._lib.mcpb200_last_error(h.raw)
+
+
+def test_solve_argument_validation(readme_mcp):
+    from mcp_b200 import InteriorPoint, solve
+    with pytest.raises(ValueError):
+        solve(InteriorPoint(), readme_mcp, np.zeros(3))                  # wrong θ length
+    with pytest.raises(ValueError):
+        solve(InteriorPoint(), readme_mcp, np.zeros((2, 4)), x0=np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        solve(InteriorPoint(), readme_mcp, np.zeros(2), linear_solve_algorithm="KLU")
+    with pytest.raises(TypeError):
+        solve(object(), readme_mcp, np.zeros(2))
