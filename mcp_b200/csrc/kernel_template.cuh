@@ -17,9 +17,9 @@
 //
 // Macros provided by the prologue:
 //   NX NY NT NRED KL KU WC WR WS1 WSS NRHS_SENS NJV NJTV ND THETA_IN_SMEM
-//   SOLVE_WARPS SENS_WARPS  SOLVE_SMEM_DOUBLES SENS_SMEM_DOUBLES (per warp)
-//   SOLVE_SCRATCH SENS_SCRATCH (doubles per warp)  HAS_JT
-// Tables: D_RC D_TP (dests), T_COEF T_A T_B T_K (terms), R_GROW R_PTR R_CODE R_K R_COEF (rhs),
+//   SOLVE_WARPS SENS_WARPS  SOLVE_SMEM_DOUBLES SENS_SMEM_DOUBLES (per warp)  SHARED_TABLE_DOUBLES (per CTA)
+//   SOLVE_SCRATCH SENS_SCRATCH CVAL_DOUBLES (doubles per warp)  HAS_JT
+// Tables: D_ROWPTR D_CPOS D_TP (dests), T_COEF T_I (terms), R_GROW R_PTR R_CODE R_K R_COEF (rhs),
 //   H_PTR H_CODE H_COL H_COEF (H_x rows), PERM, Q_PTR Q_ROW Q_CODE Q_COEF (θ-Jacobian by column)
 
 #define FULLMASK 0xffffffffu
@@ -85,78 +85,124 @@ __device__ __forceinline__ double warp_nanmax(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Assembly of the condensed matrix C = G_x + tol·I − G_y D⁻¹ H_x into banded global rows.
-// Cg: NRED rows × WS doubles; column c of row i is stored at circular position c % WC, the RHS
-// columns at positions WC … WC+NRHS-1.
+// CTA-shared tables (first SHARED_TABLE_DOUBLES doubles of dynamic shared memory): ROWPTR_S[NRED+1]
+// (first dest of each condensed row) and CPOS_S[ND] (circular window position of each dest).
 // ------------------------------------------------------------------------------------------------
-template <int WS>
-__device__ __forceinline__ void assemble_matrix(double* __restrict__ Cg, const double* __restrict__ jv,
-                                                const double* __restrict__ th, const double* __restrict__ dinv,
-                                                double tol, int lane) {
-  // zero fill (scratch is padded to an even number of doubles and 16-byte aligned)
-  double2* C2 = reinterpret_cast<double2*>(Cg);
-  for (int i = lane; i < (NRED * WS + 1) / 2; i += 32) C2[i] = make_double2(0.0, 0.0);
-  __syncwarp();
-  for (int d = lane; d < ND; d += 32) {
-    const unsigned rc = (unsigned)D_RC[d];
-    const int tp = D_TP[d];
-    const int t1 = D_TP[d + 1] & 0x7fffffff;
-    double acc = (tp < 0) ? tol : 0.0;  // sign bit of D_TP marks a diagonal dest
-    for (int t = tp & 0x7fffffff; t < t1; ++t) {
-      double v = T_COEF[t] * opval(T_A[t], jv, th);
-      const int k = T_K[t];
-      if (k >= 0) v *= dinv[k] * opval(T_B[t], jv, th);
-      acc += v;
-    }
-    Cg[(rc >> 16) * WS + (rc & 0xffff)] = acc;
-  }
+__device__ __forceinline__ void load_shared_tables(double* smem_base) {
+  int* rowptr = reinterpret_cast<int*>(smem_base);
+  unsigned short* cpos = reinterpret_cast<unsigned short*>(rowptr + NRED + 1);
+  for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = D_ROWPTR[i];
+  for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)D_CPOS[i];
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
+// Assembly of the condensed matrix C = G_x + tol·I − G_y D⁻¹ H_x: one value per structural non-zero
+// ("dest", sorted by row then column) into the compact L2-resident array Cval[ND].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, double* __restrict__ tmp,
+                                                const double* __restrict__ jv, const double* __restrict__ th,
+                                                const double* __restrict__ dinv, double tol, int lane) {
+  // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
+#if ASM_TWO_PHASE
+  // phase A, term-parallel (all table loads independent and coalesced): tmp[t] = coef·val(a)·[D⁻¹_k·val(b)]
+  for (int t = lane; t < NTERMS; t += 32) {
+    const int4 ti = T_I[t];  // {a, b, k, -}
+    double v = T_COEF[t] * opval(ti.x, jv, th);
+    if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
+    tmp[t] = v;
+  }
+  __syncwarp();
+  // phase B, dest-parallel: sum the (contiguous) terms of each dest
+  for (int d = lane; d < ND; d += 32) {
+    const int tp = D_TP[d];
+    const int t1 = D_TP[d + 1] & 0x7fffffff;
+    double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
+    for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t];
+    Cval[d] = acc;
+  }
+  __syncwarp();
+#else
+  for (int d = lane; d < ND; d += 32) {
+    const int tp = D_TP[d];
+    const int t1 = D_TP[d + 1] & 0x7fffffff;
+    double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
+    for (int t = tp & 0x7fffffff; t < t1; ++t) {
+      const int4 ti = T_I[t];
+      double v = T_COEF[t] * opval(ti.x, jv, th);
+      if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
+      acc += v;
+    }
+    Cval[d] = acc;
+  }
+#endif
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // Banded LU with partial pivoting on a sliding window held in shared memory, forward substitution
-// folded into the elimination (RHS columns ride along as extra window columns), then back substitution
-// streaming the U rows back from the scratch.  One warp.
+// folded into the elimination (RHS columns ride along as extra window columns), then a column-sweep
+// back substitution.  One warp.
 //
-//   W   : shared, WR slots × WS doubles.  Slots are never swapped: the pivot's slot is retired and
-//         re-used by the row entering the window, which is what makes pivoting free of data movement.
-//   Cg  : global scratch, NRED × WS; holds the assembled rows on entry, the U rows (with the
-//         reciprocal pivot on the diagonal position) on exit.
-//   sol : shared, NRHS × NRED (sol[q*NRED + c]) in the permuted ordering.
-// Lanes own window COLUMNS (positions lane, lane+32, …); rows with a zero multiplier are skipped
-// warp-uniformly, so sparsity inside the band costs nothing.
+//   W    : shared, WR slots × WS doubles (WS ≡ 2 mod 4 ⇒ row-strided 128-bit accesses are conflict free).  Column c
+//          of a row lives at circular position c % WC, the RHS at WC … WC+NRHS-1.  Slots are never
+//          swapped: the pivot's slot is retired and re-used by the row entering the window, so partial
+//          pivoting moves no data.
+//   Cval : global, the assembled non-zeros (row-sorted); rows are scattered into the window as they enter.
+//   UT   : global scratch, NRED × WC: U stored TRANSPOSED, UT[c*WC + (c-i)] = U[i][c], with the
+//          reciprocal pivot at offset 0, so that the back substitution reads one contiguous row per
+//          column and needs no warp reduction.
+//   sol  : shared, NRHS × NRED: right-hand sides on entry, solution on exit (permuted ordering).
+// Lanes own window ROWS during the elimination (all rows update in parallel, zero multipliers are
+// predicated off) and consecutive rows during the back-substitution sweep.
 // Returns 0, or 1 if a pivot is zero / non-finite (the reference's `:failed` retcode branch,
 // src/solver.jl:84-88).
 // ------------------------------------------------------------------------------------------------
 template <int NRHS, int WS>
-__device__ int band_solve(double* __restrict__ W, double* __restrict__ Cg, double* __restrict__ sol, int lane) {
-  constexpr int CPL = (WC + NRHS + 31) / 32;  // window positions per lane (matrix + rhs)
-  constexpr int CPW = (WC + 31) / 32;         // matrix positions per lane
-  constexpr int RPL = (WR + 31) / 32;         // row slots per lane (pivot search / multipliers)
-  constexpr int WPL = (WS + 31) / 32;         // row copy chunks per lane
+__device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cval, double* __restrict__ UT,
+                          double* __restrict__ sol, const int* __restrict__ rowptr,
+                          const unsigned short* __restrict__ cpos, int lane) {
+  constexpr int CPW = (WC + 31) / 32;  // matrix positions per lane
+  constexpr int RPL = (WR + 31) / 32;  // row slots per lane
+  constexpr int WPL = (WS + 31) / 32;
 
   // ---- initial window: rows 0 … WR-1 -----------------------------------------------------------
-  for (int r = 0; r < WR; ++r)
-    for (int q = lane; q < WS; q += 32) W[r * WS + q] = Cg[r * WS + q];
-  int ext[RPL];  // last structurally non-zero column of the row in my slots
-#pragma unroll
-  for (int k = 0; k < RPL; ++k) {
-    const int r = lane + 32 * k;
-    ext[k] = (r < WR) ? min(r + KU, NRED - 1) : -1;
+  for (int i = lane; i < WR * WS; i += 32) W[i] = 0.0;
+  __syncwarp();
+  for (int r = 0; r < WR; ++r) {
+    for (int e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) W[r * WS + cpos[e]] = Cval[e];
+    if (lane < NRHS) W[r * WS + WC + lane] = sol[lane * NRED + r];
   }
   __syncwarp();
 
+  constexpr int NP = (WC + NRHS + 1) / 2;  // position pairs swept per row (matrix + rhs columns)
+  constexpr int PB = (NP < 9) ? NP : 9;    // pairs per register batch
+  static_assert(2 * NP <= WS, "row stride must cover the padded position pairs");
+
   int cj = 0;  // j % WC
   for (int j = 0; j < NRED; ++j) {
-    // prefetch the row that will enter the window at the end of this step
+    // prefetch the non-zeros of the row that enters the window at the end of this step
     const int ienter = j + WR;
-    double pre[WPL];
+    int e0 = 0, e1 = 0;
+    if (ienter < NRED) {
+      e0 = rowptr[ienter];
+      e1 = rowptr[ienter + 1];
+    }
+    double pre[CPW];
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      const int q = lane + 32 * k;
-      pre[k] = (ienter < NRED && q < WS) ? Cg[ienter * WS + q] : 0.0;
+    for (int k = 0; k < CPW; ++k) {
+      const int e = e0 + lane + 32 * k;
+      pre[k] = (e < e1) ? Cval[e] : 0.0;
     }
 
-    // ---- pivot search over column j: max |a| with 12-bit-truncated mantissa, slot in the low byte ----
+    // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, slot in the low byte ----
     unsigned best = 0;
     double m[RPL];
 #pragma unroll
@@ -170,133 +216,145 @@ __device__ int band_solve(double* __restrict__ W, double* __restrict__ Cg, doubl
     }
     best = __reduce_max_sync(FULLMASK, best);
     const int p = 255 - (int)(best & 0xffu);
-    const double piv = W[p * WS + cj];
-    if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1.0e300 * 1.0e300)) return 1;  // zero, NaN or Inf pivot
-    const double rp = 1.0 / piv;
-
-    int extp = ext[0];
+    double piv = m[0];
 #pragma unroll
     for (int k = 1; k < RPL; ++k)
-      if ((p >> 5) == k) extp = ext[k];
-    extp = __shfl_sync(FULLMASK, extp, p & 31);
-    const int span = extp - j;
+      if ((p >> 5) == k) piv = m[k];
+    piv = __shfl_sync(FULLMASK, piv, p & 31);
+    if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1.0e300 * 1.0e300)) return 1;  // zero, NaN or Inf pivot
+    const double rp = 1.0 / piv;
+    double* Wp = W + p * WS;
+    // Invariant: every entry of a window row outside its structural extent is exactly zero, so the
+    // update can sweep ALL positions with static code; only the pivot's own position must read as zero.
+    if (lane == 0) Wp[cj] = 0.0;
+    __syncwarp();
 
-    // ---- my columns of the pivot row ------------------------------------------------------------
-    double u[CPL];
-    bool act[CPL];
+    // ---- retire the pivot row: U row j goes out transposed, its RHS into sol ------------------------
+    {
+      const int tmax = min(WC - 1, NRED - 1 - j);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const int q = lane + 32 * k;
-      if (q < WC) {
-        int d = q - cj;
-        if (d < 0) d += WC;
-        act[k] = (d >= 1) && (d <= span);
-      } else {
-        act[k] = (q < WC + NRHS);
+      for (int k = 0; k < CPW; ++k) {
+        const int q = lane + 32 * k;
+        if (q < WC) {
+          int d = q - cj;
+          if (d < 0) d += WC;
+          if (d <= tmax) UT[(j + d) * WC + d] = (d == 0) ? rp : Wp[q];
+        }
       }
-      u[k] = act[k] ? W[p * WS + q] : 0.0;
+      if (lane < NRHS) sol[lane * NRED + j] = Wp[WC + lane];
     }
 
-    // ---- retire the pivot row: U row j (reciprocal pivot on the diagonal) -------------------------
+    // ---- eliminate column j: every row (lanes own rows) minus multiplier × pivot row -----------------
+    // Rows with a zero multiplier (and the pivot row itself, whose multiplier is forced to zero) are
+    // rewritten unchanged: no per-lane branches, 128-bit conflict-free accesses (WS ≡ 2 mod 4).
+    {
+      const double2* Wp2 = reinterpret_cast<const double2*>(Wp);
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      const int q = lane + 32 * k;
-      if (q < WS) {
-        double v = W[p * WS + q];
-        if (q == cj) v = rp;
-        Cg[j * WS + q] = v;
+      for (int k = 0; k < RPL; ++k) {
+        const int r = lane + 32 * k;
+        m[k] = (r < WR && r != p) ? -(m[k] * rp) : 0.0;
       }
-    }
-
-    // ---- eliminate column j from every other row with a non-zero entry ---------------------------
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) {
-      const bool nz = (m[k] != 0.0) && (lane + 32 * k != p);
-      unsigned mask = __ballot_sync(FULLMASK, nz);
-      if (nz) ext[k] = max(ext[k], extp);
-      while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const double mm = __shfl_sync(FULLMASK, m[k], src) * rp;
-        double* Wr = W + (src + 32 * k) * WS;
+      for (int b0 = 0; b0 < NP; b0 += PB) {
+        double2 u[PB];
 #pragma unroll
-        for (int kk = 0; kk < CPL; ++kk) {
-          if (act[kk]) {
-            const int q = lane + 32 * kk;
-            Wr[q] = fma(-mm, u[kk], Wr[q]);
+        for (int i = 0; i < PB; ++i)
+          if (b0 + i < NP) u[i] = Wp2[b0 + i];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const int r = lane + 32 * k;
+          if (r < WR) {
+            double2* Wr2 = reinterpret_cast<double2*>(W + r * WS);
+            double2 a[PB];
+#pragma unroll
+            for (int i = 0; i < PB; ++i)
+              if (b0 + i < NP) a[i] = Wr2[b0 + i];
+#pragma unroll
+            for (int i = 0; i < PB; ++i)
+              if (b0 + i < NP) {
+                a[i].x = fma(m[k], u[i].x, a[i].x);
+                a[i].y = fma(m[k], u[i].y, a[i].y);
+                Wr2[b0 + i] = a[i];
+              }
           }
         }
-        if (lane == 0) Wr[cj] = 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        const int r = lane + 32 * k;
+        if (r < WR && r != p) W[r * WS + cj] = 0.0;  // the eliminated entry (exactly zero by construction)
       }
     }
     __syncwarp();
 
     // ---- the entering row takes the retired slot ---------------------------------------------------
+    {
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      const int q = lane + 32 * k;
-      if (q < WS) W[p * WS + q] = pre[k];
-    }
-    if (lane == (p & 31)) {
-      const int e = (ienter < NRED) ? min(ienter + KU, NRED - 1) : -1;
+      for (int k = 0; k < WPL; ++k) {
+        const int q = lane + 32 * k;
+        if (q < WS) Wp[q] = 0.0;
+      }
+      __syncwarp();
 #pragma unroll
-      for (int k = 0; k < RPL; ++k)
-        if ((p >> 5) == k) ext[k] = e;
+      for (int k = 0; k < CPW; ++k) {
+        const int e = e0 + lane + 32 * k;
+        if (e < e1) Wp[cpos[e]] = pre[k];
+      }
+      if (lane < NRHS && ienter < NRED) Wp[WC + lane] = sol[lane * NRED + ienter];
     }
     __syncwarp();
     cj = (cj + 1 == WC) ? 0 : cj + 1;
   }
 
-  // ---- back substitution -----------------------------------------------------------------------------
-  __threadfence_block();
-  cj = (NRED - 1) % WC;
-  double cur[CPW], rhs_cur = 0.0, nxt[CPW], rhs_nxt = 0.0;
+  // ---- back substitution: column sweep, x_j = rhs_j / u_jj then rhs_i −= U[i][j] x_j for i < j.
+  // The columns of U (rows of UT) stream back through a RING_D-deep cp.async ring that re-uses the
+  // window's shared memory, so the L2/HBM latency of the scratch is off the critical path.
+  {
+    double* ring = W;
+    auto issue = [&](int col) {
+      if (col >= 0) {
+        const double* src = UT + (size_t)col * WC;
+        double* dst = ring + ((NRED - 1 - col) % RING_D) * WC;
 #pragma unroll
-  for (int k = 0; k < CPW; ++k) {
-    const int q = lane + 32 * k;
-    cur[k] = (q < WC) ? Cg[(NRED - 1) * WS + q] : 0.0;
-  }
-  if (lane < NRHS) rhs_cur = Cg[(NRED - 1) * WS + WC + lane];
-  for (int j = NRED - 1; j >= 0; --j) {
-    if (j > 0) {
-#pragma unroll
-      for (int k = 0; k < CPW; ++k) {
-        const int q = lane + 32 * k;
-        nxt[k] = (q < WC) ? Cg[(j - 1) * WS + q] : 0.0;
-      }
-      if (lane < NRHS) rhs_nxt = Cg[(j - 1) * WS + WC + lane];
-    }
-    const int span = min(WC - 1, NRED - 1 - j);
-    double acc[NRHS];
-#pragma unroll
-    for (int q = 0; q < NRHS; ++q) acc[q] = 0.0;
-    double rdiag = 0.0;
-#pragma unroll
-    for (int k = 0; k < CPW; ++k) {
-      const int q = lane + 32 * k;
-      if (q < WC) {
-        int d = q - cj;
-        if (d < 0) d += WC;
-        if (d == 0) rdiag = cur[k];
-        if (d >= 1 && d <= span) {
-#pragma unroll
-          for (int rq = 0; rq < NRHS; ++rq) acc[rq] = fma(cur[k], sol[rq * NRED + j + d], acc[rq]);
+        for (int k = 0; k < CPW; ++k) {
+          const int t = lane + 32 * k;
+          if (t < WC) cp_async8(dst + t, src + t);
         }
       }
-    }
-    rdiag = __shfl_sync(FULLMASK, rdiag, cj & 31);
-    double mine = 0.0;
-#pragma unroll
-    for (int rq = 0; rq < NRHS; ++rq) {
-      const double tot = warp_sum(acc[rq]);
-      if (lane == rq) mine = tot;
-    }
-    if (lane < NRHS) sol[lane * NRED + j] = (rhs_cur - mine) * rdiag;
+      cp_async_commit();  // (possibly empty) group: keeps the group count uniform
+    };
     __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < RING_D - 1; ++i) issue(NRED - 1 - i);
+#pragma unroll 1
+    for (int j = NRED - 1; j >= 0; --j) {
+      issue(j - (RING_D - 1));
+      cp_async_wait<RING_D - 1>();
+      __syncwarp();
+      const double* Uj = ring + ((NRED - 1 - j) % RING_D) * WC;
+      const double rd = Uj[0];
+      double ut[CPW];
 #pragma unroll
-    for (int k = 0; k < CPW; ++k) cur[k] = nxt[k];
-    rhs_cur = rhs_nxt;
-    cj = (cj == 0) ? WC - 1 : cj - 1;
+      for (int k = 0; k < CPW; ++k) {
+        const int t = lane + 1 + 32 * k;
+        ut[k] = (t < WC) ? Uj[t] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) {
+        double xj = 0.0;
+        if (lane == 0) {
+          xj = sol[q * NRED + j] * rd;
+          sol[q * NRED + j] = xj;
+        }
+        xj = __shfl_sync(FULLMASK, xj, 0);
+#pragma unroll
+        for (int k = 0; k < CPW; ++k) {
+          const int t = lane + 1 + 32 * k;
+          if (t < WC && t <= j) sol[q * NRED + j - t] = fma(-ut[k], xj, sol[q * NRED + j - t]);
+        }
+      }
+      __syncwarp();
+    }
   }
   return 0;
 }
@@ -323,7 +381,10 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  double* S = smem + (size_t)warp * SOLVE_SMEM_DOUBLES;
+  load_shared_tables(smem);
+  const int* rowptr = reinterpret_cast<const int*>(smem);
+  const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
+  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)warp * SOLVE_SMEM_DOUBLES;
   double* x = S + SOLVE_OFF_X;
   double* y = S + SOLVE_OFF_Y;
   double* s = S + SOLVE_OFF_S;
@@ -336,7 +397,8 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
 #if THETA_IN_SMEM
   double* th = S + SOLVE_OFF_TH;
 #endif
-  double* Cg = p.scratch + ((size_t)blockIdx.x * SOLVE_WARPS + warp) * SOLVE_SCRATCH;
+  double* Cval = p.scratch + ((size_t)blockIdx.x * SOLVE_WARPS + warp) * SOLVE_SCRATCH;
+  double* UT = Cval + CVAL_DOUBLES;
   const double tol = p.tol;
 
   for (;;) {
@@ -385,14 +447,15 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
         __syncwarp();
 
         // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
-        assemble_matrix<WS1>(Cg, jv, th, dinv, tol, lane);
         for (int i = lane; i < NRED; i += 32) {
           double r = -gh[R_GROW[i]];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
-          Cg[i * WS1 + WC] = r;
+          sol[i] = r;
         }
+        __syncwarp();   // gh (aliased onto the window) is dead from here on: the window becomes scratch
+        assemble_matrix(Cval, W, jv, th, dinv, tol, lane);
         __syncwarp();
-        if (band_solve<1, WS1>(W, Cg, sol, lane)) {          // :84-88
+        if (band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, lane)) {          // :84-88
           status = 1;
           break;
         }
@@ -454,7 +517,10 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  double* S = smem + (size_t)warp * SENS_SMEM_DOUBLES;
+  load_shared_tables(smem);
+  const int* rowptr = reinterpret_cast<const int*>(smem);
+  const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
+  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)warp * SENS_SMEM_DOUBLES;
   double* x = S + SENS_OFF_X;
   double* y = S + SENS_OFF_Y;
   double* s = S + SENS_OFF_S;
@@ -467,7 +533,8 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
 #if THETA_IN_SMEM
   double* th = S + SENS_OFF_TH;
 #endif
-  double* Cg = p.scratch + ((size_t)blockIdx.x * SENS_WARPS + warp) * SENS_SCRATCH;
+  double* Cval = p.scratch + ((size_t)blockIdx.x * SENS_WARPS + warp) * SENS_SCRATCH;
+  double* UT = Cval + CVAL_DOUBLES;
   constexpr int NZ = NX + 2 * NY;
 
   for (;;) {
@@ -496,7 +563,8 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
     for (int q0 = 0; q0 < NT; q0 += NRHS_SENS) {
       const int nq = min(NRHS_SENS, NT - q0);
       for (int i = lane; i < NRHS_SENS * NY; i += 32) wq[i] = 0.0;
-      assemble_matrix<WSS>(Cg, jv, th, dinv, 0.0, lane);
+      for (int i = lane; i < NRHS_SENS * NRED; i += 32) sol[i] = 0.0;
+      assemble_matrix(Cval, W, jv, th, dinv, 0.0, lane);
       __syncwarp();
       // right-hand sides r = −∇F_θ[:, q]:  G rows go to the reduced rhs, H rows to w = D⁻¹ r₂
       for (int rq = 0; rq < nq; ++rq) {
@@ -504,21 +572,21 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
         for (int e = Q_PTR[q] + lane; e < Q_PTR[q + 1]; e += 32) {
           const double v = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
           const int row = Q_ROW[e];
-          if (row < NX) Cg[IPERM[row] * WSS + WC + rq] = v;
+          if (row < NX) sol[rq * NRED + IPERM[row]] = v;
           else wq[rq * NY + (row - NX)] = dinv[row - NX] * v;
         }
       }
       __syncwarp();
       for (int i = lane; i < NRED; i += 32) {
         for (int rq = 0; rq < nq; ++rq) {
-          double r = Cg[i * WSS + WC + rq];
+          double r = sol[rq * NRED + i];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
             r -= R_COEF[e] * opval(R_CODE[e], jv, th) * wq[rq * NY + R_K[e]];
-          Cg[i * WSS + WC + rq] = r;
+          sol[rq * NRED + i] = r;
         }
       }
       __syncwarp();
-      if (band_solve<NRHS_SENS, WSS>(W, Cg, sol, lane)) {
+      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, lane)) {
         bad = 1;
         break;
       }

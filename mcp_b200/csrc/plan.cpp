@@ -259,7 +259,12 @@ Operand classify(const Plan& P, int node, std::map<int, int>& slot_of_node, std:
   return {1.0, it->second};
 }
 
-int odd_at_least(int v) { return (v & 1) ? v : v + 1; }
+// smallest stride ≥ v with stride ≡ 2 (mod 4): rows are 16-byte aligned and lanes striding over rows hit
+// distinct 16-byte bank groups, so 128-bit shared-memory accesses are conflict free
+int stride_for(int v) {
+  int s = (v + 1) & ~1;
+  return (s % 4 == 2) ? s : s + 2;
+}
 
 }  // namespace
 
@@ -409,8 +414,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
   if (N >= 65536 || P.WC >= 65536) return fail(MCPB200_ERR_UNSUPPORTED, "reduced dimension ≥ 65536");
   P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
-  P.WS1 = odd_at_least(P.WC + 1);
-  P.WSS = odd_at_least(P.WC + P.nrhs_sens);
+  P.WS1 = stride_for(P.WC + 1);
+  P.WSS = stride_for(P.WC + P.nrhs_sens);
 
   // ---- assembly tables (new ordering) -------------------------------------------------------------------
   {
@@ -426,13 +431,19 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       P.d_row.push_back(dd.row);
       P.d_cpos.push_back(dd.col % P.WC);
       P.d_diag.push_back(dd.row == dd.col);
+      double base = 0.0;
       for (auto& t : *dd.terms) {
+        if (t.a == -1 && t.k < 0) {  // numeric constant: folded on the host
+          base += t.coef;
+          continue;
+        }
         P.t_coef.push_back(t.coef);
         P.t_a.push_back(t.a);
         P.t_b.push_back(t.b);
         P.t_k.push_back(t.k);
       }
       P.d_tptr.push_back((int)P.t_coef.size());
+      P.d_base.push_back(base);
     }
     // rhs rows
     std::vector<std::vector<Entry>> gy_by_row(nx);
@@ -481,15 +492,19 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     lay << "#define " << name << " " << off << "\n";
     off = even(off + n);
   };
+  // G/H values are consumed (residual norms, w, condensed rhs) before the window is filled, so `gh`
+  // shares the window's storage whenever it fits
+  const bool gh_alias = (int64_t)P.R * P.WS1 >= nx + ny;
   place("SOLVE_OFF_X", nx);
   place("SOLVE_OFF_Y", ny);
   place("SOLVE_OFF_S", ny);
-  place("SOLVE_OFF_GH", nx + ny);
+  if (!gh_alias) place("SOLVE_OFF_GH", nx + ny);
   place("SOLVE_OFF_JV", njv);
   place("SOLVE_OFF_DINV", ny);
   place("SOLVE_OFF_W", ny);
   place("SOLVE_OFF_SOL", N);
   if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
+  if (gh_alias) lay << "#define SOLVE_OFF_GH " << off << "\n";
   place("SOLVE_OFF_WIN", (int64_t)P.R * P.WS1);
   const int64_t solve_doubles = off;
   off = 0;
@@ -504,8 +519,10 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (P.theta_in_smem) place("SENS_OFF_TH", nt);
   place("SENS_OFF_WIN", (int64_t)P.R * P.WSS);
   const int64_t sens_doubles = off;
+  const int64_t nd = (int64_t)P.d_row.size();
+  const int64_t shared_table_doubles = even(((int64_t)(N + 1) * 4 + nd * 2 + 7) / 8);
   auto warps_for = [&](int64_t doubles) {
-    int64_t w = kSmemBudget / (doubles * 8);
+    int64_t w = (kSmemBudget - shared_table_doubles * 8) / (doubles * 8);
     return (int)std::max<int64_t>(0, std::min<int64_t>(w, 16));
   };
   P.ipc_solve = warps_for(solve_doubles);
@@ -516,10 +533,11 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
              (long long)(std::max(solve_doubles, sens_doubles) * 8), kSmemBudget);
     return fail(MCPB200_ERR_UNSUPPORTED, buf);
   }
-  P.smem_solve = solve_doubles * 8 * P.ipc_solve;
-  P.smem_sens = sens_doubles * 8 * P.ipc_sens;
-  P.scratch_doubles_solve = even((int64_t)N * P.WS1) + 2;
-  P.scratch_doubles_sens = even((int64_t)N * P.WSS) + 2;
+  P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
+  P.smem_sens = (shared_table_doubles + sens_doubles * P.ipc_sens) * 8;
+  const int64_t cval_doubles = even(nd) + 2;
+  P.scratch_doubles_solve = cval_doubles + even((int64_t)N * P.WC) + 2;
+  P.scratch_doubles_sens = P.scratch_doubles_solve;
   // banded LU with partial pivoting + forward/back substitution, dense-in-band count
   {
     const double kl = P.kl, kuu = std::min(P.kl + P.ku, N - 1);
@@ -537,19 +555,36 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   os << "#define SOLVE_WARPS " << P.ipc_solve << "\n#define SENS_WARPS " << P.ipc_sens << "\n";
   os << "#define SOLVE_SMEM_DOUBLES " << solve_doubles << "\n#define SENS_SMEM_DOUBLES " << sens_doubles << "\n";
   os << "#define SOLVE_SCRATCH " << P.scratch_doubles_solve << "\n#define SENS_SCRATCH " << P.scratch_doubles_sens << "\n";
+  {
+    const int64_t win1 = (int64_t)P.R * P.WS1, wins = (int64_t)P.R * P.WSS, nterms = (int64_t)P.t_coef.size();
+    // the window's storage doubles as the term buffer of the two-phase assembly and as the cp.async ring
+    os << "#define NTERMS " << nterms << "\n#define ASM_TWO_PHASE " << ((nterms <= std::min(win1, wins)) ? 1 : 0) << "\n";
+    os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / P.WC)) << "\n";
+  }
+  os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
   os << lay.str();
   {
-    std::vector<int32_t> rc(P.d_row.size()), tp(P.d_tptr.size());
-    for (size_t i = 0; i < P.d_row.size(); ++i) rc[i] = (P.d_row[i] << 16) | P.d_cpos[i];
+    std::vector<int32_t> tp(P.d_tptr.size()), rowptr(N + 1, 0);
     for (size_t i = 0; i < P.d_tptr.size(); ++i)
       tp[i] = P.d_tptr[i] | ((i < P.d_diag.size() && P.d_diag[i]) ? (int32_t)0x80000000 : 0);
-    emit_table(os, "int", "D_RC", rc);
+    for (size_t i = 0; i < P.d_row.size(); ++i) rowptr[P.d_row[i] + 1]++;   // dests are sorted by row
+    for (int i = 0; i < N; ++i) rowptr[i + 1] += rowptr[i];
+    emit_table(os, "int", "D_ROWPTR", rowptr);
+    emit_table(os, "int", "D_CPOS", P.d_cpos);
     emit_table(os, "int", "D_TP", tp);
+    emit_table(os, "double", "D_BASE", P.d_base, true);
   }
   emit_table(os, "double", "T_COEF", P.t_coef, true);
-  emit_table(os, "int", "T_A", P.t_a);
-  emit_table(os, "int", "T_B", P.t_b);
-  emit_table(os, "int", "T_K", P.t_k);
+  {
+    os << "__device__ const int4 T_I[" << std::max<size_t>(P.t_a.size(), 1) << "] = {";
+    if (P.t_a.empty()) os << "{0,0,0,0}";
+    for (size_t i = 0; i < P.t_a.size(); ++i) {
+      if (i) os << ",";
+      if (i % 8 == 7) os << "\n";
+      os << "{" << P.t_a[i] << "," << P.t_b[i] << "," << P.t_k[i] << ",0}";
+    }
+    os << "};\n";
+  }
   emit_table(os, "int", "R_GROW", P.r_grow);
   emit_table(os, "int", "R_PTR", P.r_ptr);
   emit_table(os, "int", "R_CODE", P.r_code);
