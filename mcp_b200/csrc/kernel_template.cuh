@@ -1,7 +1,7 @@
 // kernel_template.cuh — hand-written sm_100a kernels of the batched interior-point MCP solver.
 //
 // This file is NOT compiled on its own: plan.cpp prepends a generated prologue (problem-size macros,
-// assembly tables as __device__ const arrays, and the device functions mcp_eval_newton / mcp_eval_sens
+// assembly tables as __device__ const arrays, and the device functions mcp_eval_newton_par / mcp_eval_sens_par
 // lowered from the traced G, H and Jacobian entries) and hands the result to NVRTC for sm_100a.
 //
 // One WARP owns one problem instance for its whole solve (persistent over Newton iterations): the
@@ -430,7 +430,7 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
       status = 0;                                            // :73
       while (kkt > eps && inner < p.max_inner) {             // :75
         // F and the Jacobian entries at the current iterate (:79-80)
-        if (lane == 0) mcp_eval_newton(x, y, th, gh, jv);
+        mcp_eval_newton_par(lane, x, y, th, gh, jv);   // lane i evaluates output group i
         __syncwarp();
         double fmax_ = 0.0;
         for (int i = lane; i < NX; i += 32) fmax_ = nanmax(fmax_, fabs(gh[i]));
@@ -553,7 +553,7 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
       s[i] = p.s[inst * NY + i];
     }
     __syncwarp();
-    if (lane == 0) mcp_eval_sens(x, y, th, jv, jtv);
+    mcp_eval_sens_par(lane, x, y, th, jv, jtv);
     __syncwarp();
     for (int k = lane; k < NY; k += 32) dinv[k] = y[k] / s[k];  // D⁻¹ with D = s/y (tol = 0)
     if (p.z_p)

@@ -201,43 +201,107 @@ struct Emitter {
     }
   }
 
-  // emits `const double vN = …;` for every non-leaf node the roots need
+  // Emits `const double vN = …;` for every non-leaf node the roots need, depth-first per root: each
+  // output's expression tree is emitted right before its use, which keeps live ranges (and hence register
+  // pressure / spills of the generated device function) short; shared sub-expressions are emitted once.
   void body(std::ostringstream& os, const std::vector<int32_t>& roots) const {
-    std::vector<char> need(P.op.size(), 0);
-    std::vector<int> stack(roots.begin(), roots.end());
-    while (!stack.empty()) {
-      int n = stack.back();
-      stack.pop_back();
-      if (need[n]) continue;
-      need[n] = 1;
-      const int op = P.op[n];
-      if (is_binary(op)) {
-        stack.push_back(P.a[n]);
-        stack.push_back(P.b[n]);
-      } else if (!is_leaf(op)) {
-        stack.push_back(P.a[n]);
+    std::vector<char> done(P.op.size(), 0);
+    std::vector<std::pair<int, int>> stack;  // (node, next operand to visit)
+    for (int root : roots) {
+      if (done[root] || is_leaf(P.op[root])) continue;
+      stack.push_back({root, 0});
+      while (!stack.empty()) {
+        auto& top = stack.back();
+        const int n = top.first;
+        const int op = P.op[n];
+        const int nops = is_binary(op) ? 2 : 1;
+        if (top.second < nops) {
+          const int child = (top.second == 0) ? P.a[n] : P.b[n];
+          ++top.second;
+          if (!done[child] && !is_leaf(P.op[child])) stack.push_back({child, 0});
+          continue;
+        }
+        stack.pop_back();
+        if (done[n]) continue;
+        done[n] = 1;
+        statement(os, n);
       }
     }
-    for (size_t n = 0; n < P.op.size(); ++n) {
-      if (!need[n] || is_leaf(P.op[n])) continue;
-      const std::string A = operand(P.a[n]);
-      os << "  const double v" << n << " = ";
-      switch (P.op[n]) {
-        case MCPB200_OP_ADD: os << A << " + " << operand(P.b[n]); break;
-        case MCPB200_OP_SUB: os << A << " - " << operand(P.b[n]); break;
-        case MCPB200_OP_MUL: os << A << " * " << operand(P.b[n]); break;
-        case MCPB200_OP_DIV: os << A << " / " << operand(P.b[n]); break;
-        case MCPB200_OP_NEG: os << "-" << A; break;
-        case MCPB200_OP_SQRT: os << "sqrt(" << A << ")"; break;
-        case MCPB200_OP_EXP: os << "exp(" << A << ")"; break;
-        case MCPB200_OP_LOG: os << "log(" << A << ")"; break;
-        case MCPB200_OP_SIN: os << "sin(" << A << ")"; break;
-        case MCPB200_OP_COS: os << "cos(" << A << ")"; break;
-        case MCPB200_OP_POWI: os << "mcp_powi(" << A << ", " << P.b[n] << ")"; break;
-        default: os << "0.0"; break;
+  }
+
+  // number of not-yet-emitted interior nodes each root would add, processing roots in order
+  std::vector<int> incremental_cost(const std::vector<int32_t>& roots) const {
+    std::vector<char> done(P.op.size(), 0);
+    std::vector<int> cost(roots.size(), 1);
+    std::vector<int> stack;
+    for (size_t r = 0; r < roots.size(); ++r) {
+      stack.assign(1, roots[r]);
+      while (!stack.empty()) {
+        const int n = stack.back();
+        stack.pop_back();
+        if (done[n] || is_leaf(P.op[n])) continue;
+        done[n] = 1;
+        ++cost[r];
+        stack.push_back(P.a[n]);
+        if (is_binary(P.op[n])) stack.push_back(P.b[n]);
       }
-      os << ";\n";
     }
+    return cost;
+  }
+
+  // Emits `name`_p0 … `name`_p{K-1} (K ≤ 32 balanced, contiguous groups of outputs, each a __noinline__
+  // function with bounded register pressure) and the lane dispatcher `name`_par(lane, …): lane i evaluates
+  // group i, so the residual / Jacobian evaluation of one instance is spread over the warp.  Sub-expressions
+  // shared between groups are recomputed per group.
+  // outs[i] = {root node, "target[index]"}.
+  void partitioned(std::ostringstream& os, const std::string& name, const std::string& params,
+                   const std::string& args, const std::vector<std::pair<int32_t, std::string>>& outs) const {
+    std::vector<int32_t> roots;
+    for (auto& o : outs) roots.push_back(o.first);
+    const std::vector<int> cost = incremental_cost(roots);
+    long total = 0;
+    for (int c : cost) total += c;
+    const int K = (int)std::max<long>(1, std::min<long>(32, std::min<long>((long)outs.size(), total / 24 + 1)));
+    std::vector<size_t> begin(K + 1, outs.size());
+    begin[0] = 0;
+    {
+      long acc = 0;
+      int part = 1;
+      for (size_t i = 0; i < outs.size() && part < K; ++i) {
+        acc += cost[i];
+        if (acc * K >= total * part) begin[part++] = i + 1;
+      }
+    }
+    for (int k = 0; k < K; ++k) {
+      os << "__device__ __noinline__ void " << name << "_p" << k << "(" << params << ") {\n";
+      std::vector<int32_t> sub(roots.begin() + begin[k], roots.begin() + begin[k + 1]);
+      body(os, sub);
+      for (size_t i = begin[k]; i < begin[k + 1]; ++i) os << "  " << outs[i].second << " = " << operand(outs[i].first) << ";\n";
+      os << "}\n";
+    }
+    os << "__device__ __forceinline__ void " << name << "_par(int lane, " << params << ") {\n  switch (lane) {\n";
+    for (int k = 0; k < K; ++k) os << "    case " << k << ": " << name << "_p" << k << "(" << args << "); break;\n";
+    os << "    default: break;\n  }\n}\n";
+  }
+
+  void statement(std::ostringstream& os, int n) const {
+    const std::string A = operand(P.a[n]);
+    os << "  const double v" << n << " = ";
+    switch (P.op[n]) {
+      case MCPB200_OP_ADD: os << A << " + " << operand(P.b[n]); break;
+      case MCPB200_OP_SUB: os << A << " - " << operand(P.b[n]); break;
+      case MCPB200_OP_MUL: os << A << " * " << operand(P.b[n]); break;
+      case MCPB200_OP_DIV: os << A << " / " << operand(P.b[n]); break;
+      case MCPB200_OP_NEG: os << "-" << A; break;
+      case MCPB200_OP_SQRT: os << "sqrt(" << A << ")"; break;
+      case MCPB200_OP_EXP: os << "exp(" << A << ")"; break;
+      case MCPB200_OP_LOG: os << "log(" << A << ")"; break;
+      case MCPB200_OP_SIN: os << "sin(" << A << ")"; break;
+      case MCPB200_OP_COS: os << "cos(" << A << ")"; break;
+      case MCPB200_OP_POWI: os << "mcp_powi(" << A << ", " << P.b[n] << ")"; break;
+      default: os << "0.0"; break;
+    }
+    os << ";\n";
   }
 };
 
@@ -609,26 +673,28 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   Emitter E(P);
   // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
   os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
-  os << "__device__ __noinline__ void mcp_eval_newton(const double* __restrict__ x, const double* __restrict__ y,\n"
-        "    const double* __restrict__ th, double* __restrict__ gh, double* __restrict__ jv) {\n";
   {
-    std::vector<int32_t> roots(P.gh_nodes);
-    roots.insert(roots.end(), P.jv_nodes.begin(), P.jv_nodes.end());
-    E.body(os, roots);
-    for (int i = 0; i < nx + ny; ++i) os << "  gh[" << i << "] = " << E.operand(P.gh_nodes[i]) << ";\n";
-    for (int i = 0; i < njv; ++i) os << "  jv[" << i << "] = " << E.operand(P.jv_nodes[i]) << ";\n";
+    std::vector<std::pair<int32_t, std::string>> outs;
+    for (int i = 0; i < nx + ny; ++i) outs.push_back({P.gh_nodes[i], "gh[" + std::to_string(i) + "]"});
+    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], "jv[" + std::to_string(i) + "]"});
+    E.partitioned(os, "mcp_eval_newton",
+                  "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                  "double* __restrict__ gh, double* __restrict__ jv",
+                  "x, y, th, gh, jv", outs);
   }
-  os << "}\n";
   if (P.has_jt) {
     os << "// computed entries of ∇F_z and ∇F_θ at the solution (src/AutoDiff.jl:27-37)\n";
-    os << "__device__ __noinline__ void mcp_eval_sens(const double* __restrict__ x, const double* __restrict__ y,\n"
-          "    const double* __restrict__ th, double* __restrict__ jv, double* __restrict__ jtv) {\n";
-    std::vector<int32_t> roots(P.jv_nodes);
-    roots.insert(roots.end(), P.jtv_nodes.begin(), P.jtv_nodes.end());
-    E.body(os, roots);
-    for (int i = 0; i < njv; ++i) os << "  jv[" << i << "] = " << E.operand(P.jv_nodes[i]) << ";\n";
-    for (int i = 0; i < njtv; ++i) os << "  jtv[" << i << "] = " << E.operand(P.jtv_nodes[i]) << ";\n";
-    os << "}\n";
+    std::vector<std::pair<int32_t, std::string>> outs;
+    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], "jv[" + std::to_string(i) + "]"});
+    for (int i = 0; i < njtv; ++i) outs.push_back({P.jtv_nodes[i], "jtv[" + std::to_string(i) + "]"});
+    if (outs.empty()) {
+      os << "__device__ __forceinline__ void mcp_eval_sens_par(int, const double*, const double*, const double*, double*, double*) {}\n";
+    } else {
+      E.partitioned(os, "mcp_eval_sens",
+                    "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                    "double* __restrict__ jv, double* __restrict__ jtv",
+                    "x, y, th, jv, jtv", outs);
+    }
   }
   os << kernel_template;
   P.source = os.str();
