@@ -388,7 +388,8 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
   double* x = S + SOLVE_OFF_X;
   double* y = S + SOLVE_OFF_Y;
   double* s = S + SOLVE_OFF_S;
-  double* gh = S + SOLVE_OFF_GH;
+  double* g = S + SOLVE_OFF_G;        // G rows (aliases the window when it fits)
+  double* hh = S + SOLVE_OFF_H;       // H rows (alias w: H[k] is consumed where w[k] is produced)
   double* jv = S + SOLVE_OFF_JV;
   double* dinv = S + SOLVE_OFF_DINV;  // D⁻¹, later δs
   double* w = S + SOLVE_OFF_W;        // w, later δy
@@ -430,12 +431,12 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
       status = 0;                                            // :73
       while (kkt > eps && inner < p.max_inner) {             // :75
         // F and the Jacobian entries at the current iterate (:79-80)
-        mcp_eval_newton_par(lane, x, y, th, gh, jv);   // lane i evaluates output group i
+        mcp_eval_newton_par(lane, x, y, th, g, hh, jv);   // lane i evaluates output group i
         __syncwarp();
         double fmax_ = 0.0;
-        for (int i = lane; i < NX; i += 32) fmax_ = nanmax(fmax_, fabs(gh[i]));
+        for (int i = lane; i < NX; i += 32) fmax_ = nanmax(fmax_, fabs(g[i]));
         for (int k = lane; k < NY; k += 32) {
-          const double f2 = gh[NX + k] - s[k];         // H − s        (src/mcp.jl:78)
+          const double f2 = hh[k] - s[k];         // H − s        (src/mcp.jl:78)
           const double f3 = s[k] * y[k] - eps;         // s∘y − ϵ      (src/mcp.jl:79)
           const double yt = y[k] + tol;                // (3,3) block diag(y) + tol·I  (:81)
           const double di = 1.0 / (tol + s[k] / yt);   // D⁻¹, D = (2,2) block tol·I + S (Y+tol)⁻¹
@@ -448,11 +449,11 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
 
         // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
         for (int i = lane; i < NRED; i += 32) {
-          double r = -gh[R_GROW[i]];
+          double r = -g[R_GROW[i]];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
           sol[i] = r;
         }
-        __syncwarp();   // gh (aliased onto the window) is dead from here on: the window becomes scratch
+        __syncwarp();   // G (aliased onto the window) is dead from here on: the window becomes scratch
         assemble_matrix(Cval, W, jv, th, dinv, tol, lane);
         __syncwarp();
         if (band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, lane)) {          // :84-88
