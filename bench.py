@@ -8,7 +8,7 @@ Metric (BASELINE.json): converged MCP solves/sec over a batched θ.  Workload: t
 trajectory game (BASELINE.json configs[2], the config north_star's target is quoted on: "≥1M converged
 solves/sec of the 2-player lane-change trajectory game across 8×B200"), benchmark θ distribution and
 `tol = 1e-6`, cold start, as in /root/reference/benchmark/path.jl:8,14-17,78-87.  A "step" is one batched
-solve of `--batch` θ columns per GPU.  Scaling is weak (fixed per-GPU batch; 2^17 per GPU = 2^20 on 8).
+solve of `--batch` θ columns per GPU.  Scaling is weak (fixed per-GPU batch: 2^18 θ per GPU per step).
 
 One JSON line on stdout (rank 0):
   value     converged solves/s, whole job, θ already resident in HBM (device entry point, CUDA events)
@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lane_change")
-    ap.add_argument("--batch", type=int, default=1 << 17, help="θ columns per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 18, help="θ columns per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -298,7 +298,7 @@ def main():
                                                        "instances_per_cta", "smem_bytes_per_cta", "regs_solve")}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K},
-            "gpu_launches": K,
+            "gpu_launches": K * int(tm["launches"]),
             "clocks": clocks.summary(),
             "roofline": {"bound": "fp64", "kernel": "mcp_solve_kernel", "achieved": achieved_tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,

@@ -39,13 +39,16 @@ struct SolveParams {
   int* status_out;
   int* steps_out;
   double* scratch;
-  unsigned long long* counters;  // [0] work queue, [1] Σ newton steps, [2] # solved
+  unsigned long long* counters;  // [0] work queue, [1] Σ newton steps, [2] # solved, [3] # deferred, [4] pass-1 queue
+  int* deferred;                 // instance ids handed from pass 0 to pass 1
   double tol;
   double tightening_rate;
   double loosening_rate;
   double min_stepsize;
   int max_inner;
   int max_outer;
+  int pass;         // 0: every instance, up to `step_budget` Newton steps; 1: resume the deferred ones
+  int step_budget;  // <= 0: no deferral
 };
 
 struct SensParams {
@@ -402,31 +405,58 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
   double* UT = Cval + CVAL_DOUBLES;
   const double tol = p.tol;
 
+  // Scheduling (semantics-neutral): instances that never converge run ~30x longer than the rest (up to
+  // (max_outer-1)(max_inner-1) Newton steps) and would leave most of the GPU idle behind a long tail.
+  // Pass 0 therefore runs every instance only up to `step_budget` steps (checked at outer-iteration
+  // boundaries, where the whole solver state is (x, y, s, ϵ, kkt_error, outer_iters)), parks the rest in
+  // the output arrays and a deferred list; pass 1 (a second launch) resumes them, all long, together.
+  const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
   for (;;) {
     unsigned long long inst = 0;
-    if (lane == 0) inst = atomicAdd(p.counters, 1ULL);
+    if (lane == 0) inst = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
     inst = __shfl_sync(FULLMASK, inst, 0);
-    if (inst >= (unsigned long long)p.B) break;
+    if (p.pass) {
+      if (inst >= n_deferred) break;
+      inst = (unsigned long long)p.deferred[inst];
+    } else if (inst >= (unsigned long long)p.B) {
+      break;
+    }
 
-    // ---- load θ and the initial point (src/solver.jl:39-41,64-66) -------------------------------
+    // ---- load θ and the initial point (src/solver.jl:39-41,64-66) — or the parked state in pass 1 ----
 #if THETA_IN_SMEM
     for (int i = lane; i < NT; i += 32) th[i] = p.theta[inst * NT + i];
 #else
     const double* th = p.theta + inst * NT;
 #endif
-    for (int i = lane; i < NX; i += 32) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
-    for (int i = lane; i < NY; i += 32) {
-      y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
-      s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
-    }
-    __syncwarp();
-
     double eps = 1.0;                                        // :67
     double kkt = __longlong_as_double(0x7ff0000000000000LL);  // Inf, :68
     int status = 0;                                          // :69
     int outer = 1;                                           // :70
     int steps = 0;
+    if (p.pass) {
+      for (int i = lane; i < NX; i += 32) x[i] = p.x_out[inst * NX + i];
+      for (int i = lane; i < NY; i += 32) {
+        y[i] = p.y_out[inst * NY + i];
+        s[i] = p.s_out[inst * NY + i];
+      }
+      eps = p.eps_out[inst];
+      kkt = p.kkt_out[inst];
+      outer = p.outer_out[inst];
+      steps = p.steps_out[inst];
+    } else {
+      for (int i = lane; i < NX; i += 32) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+      for (int i = lane; i < NY; i += 32) {
+        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      }
+    }
+    __syncwarp();
+    bool parked = false;
     while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
+        parked = true;
+        break;
+      }
       int inner = 1;                                         // :72
       status = 0;                                            // :73
       while (kkt > eps && inner < p.max_inner) {             // :75
@@ -489,7 +519,7 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
       eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
       ++outer;                                                             // :114
     }
-    if (outer == p.max_outer) status = 1;                                  // :117-119
+    if (!parked && outer == p.max_outer) status = 1;                       // :117-119
 
     for (int i = lane; i < NX; i += 32) p.x_out[inst * NX + i] = x[i];
     for (int i = lane; i < NY; i += 32) {
@@ -501,9 +531,13 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
       p.eps_out[inst] = eps;
       p.outer_out[inst] = outer;
       p.status_out[inst] = status;
-      if (p.steps_out) p.steps_out[inst] = steps;
-      atomicAdd(p.counters + 1, (unsigned long long)steps);
-      if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+      p.steps_out[inst] = steps;
+      if (parked) {
+        p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+      } else {
+        atomicAdd(p.counters + 1, (unsigned long long)steps);
+        if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+      }
     }
     __syncwarp();
   }

@@ -44,8 +44,10 @@ struct SolveParams {
   int *outer_out, *status_out, *steps_out;
   double* scratch;
   unsigned long long* counters;
+  int* deferred;
   double tol, tightening_rate, loosening_rate, min_stepsize;
   int max_inner, max_outer;
+  int pass, step_budget;
 };
 struct SensParams {
   long long B;
@@ -130,7 +132,7 @@ struct DeviceState {
   CUmodule mod = nullptr;
   CUfunction f_solve = nullptr, f_sens = nullptr;
   int num_sms = 0, regs_solve = 0, regs_sens = 0;
-  DevBuf scratch, counters;
+  DevBuf scratch, counters, deferred, steps_tmp;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h1 = nullptr;
   cudaStream_t stream = nullptr;
   // staging buffers of the host entry points
@@ -303,13 +305,30 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
+  // two-pass scheduling (kernel_template.cuh): pass 0 parks instances that exceed the step budget, pass 1
+  // resumes them together.  MCPB200_PASS1_STEPS overrides the budget (0 disables the second pass).
+  int budget = 2 * std::max(p.max_inner, 1) + 24;
+  if (const char* e = getenv("MCPB200_PASS1_STEPS")) budget = atoi(e);
+  if (st->deferred.ensure((size_t)p.B * 4 + 16)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(deferred) failed");
+  p.deferred = (int*)st->deferred.p;
+  if (!p.steps_out) {
+    if (st->steps_tmp.ensure((size_t)p.B * 4 + 16)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(steps) failed");
+    p.steps_out = (int*)st->steps_tmp.p;
+  }
+  p.step_budget = budget;
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
+  p.pass = 0;
   CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, 32u * P.ipc_solve, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+  st->launches = 1;
+  if (budget > 0) {
+    p.pass = 1;
+    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, 32u * P.ipc_solve, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+    st->launches = 2;
+  }
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
   st->timed = true;
-  st->launches = 1;
   return MCPB200_OK;
 }
 
@@ -402,7 +421,7 @@ int mcpb200_destroy(mcpb200_handle h) {
   for (auto& kv : h->dev) {
     DeviceState* st = kv.second.get();
     if (cudaSetDevice(st->dev) != cudaSuccess) continue;
-    for (DevBuf* b : {&st->scratch, &st->counters, &st->theta, &st->x, &st->y, &st->s, &st->kkt, &st->eps, &st->outer,
+    for (DevBuf* b : {&st->scratch, &st->counters, &st->deferred, &st->steps_tmp, &st->theta, &st->x, &st->y, &st->s, &st->kkt, &st->eps, &st->outer,
                       &st->status, &st->steps, &st->big0, &st->big1, &st->big2, &st->big3})
       b->release();
     for (cudaEvent_t e : {st->ev0, st->ev1, st->ev_h2d0, st->ev_h2d1, st->ev_d2h1})

@@ -152,3 +152,174 @@ def test_sensitivities_degenerate_backward_error(lane_game):
         resid = Jz @ J[:, :, b] + Jt
         rowwise = np.max(np.max(np.abs(resid), axis=1) / (np.sum(np.abs(Jz), axis=1) * np.max(np.abs(J[:, :, b])) + 1e-300))
         assert rowwise < 1e-12      # (the reference-style dense QR reaches ~1e-15 here, the condensed LU ~1e-28)
+
+
+# ---- committed golden vectors (tests/golden, generated by the oracle) ------------------------------------
+import json
+import os
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name,builder", [
+    ("lane_change_seed1.npz", lambda: problems.lane_change_game().mcp),
+    ("random_qp_12x10_seed1.npz", lambda: problems.random_qp(12, 10)),
+])
+def test_against_golden_batches(name, builder):
+    d = np.load(os.path.join(GOLD, name))
+    mcp = builder()
+    sol = solve(InteriorPoint(), mcp, d["theta"], tol=float(d["tol"]))
+    np.testing.assert_array_equal(sol.status, d["status"])
+    assert np.all(np.abs(sol.newton_steps - d["newton_steps"]) <= 1)
+    assert np.all(np.abs(sol.outer_iters - d["outer_iters"]) <= 1)
+    for got, want in ((sol.x, d["x"]), (sol.y, d["y"]), (sol.s, d["s"])):
+        for b in range(want.shape[1]):
+            assert rel_err(got[:, b], want[:, b]) <= RTOL
+
+
+def test_against_golden_small(readme_mcp, clamp_game):
+    with open(os.path.join(GOLD, "small.json")) as f:
+        g = json.load(f)
+    gb = g["readme_qp_batch"]
+    Θ = np.array(gb["theta"]).T
+    sol = solve(InteriorPoint(), readme_mcp, Θ)
+    for b, ref in enumerate(gb["sols"]):
+        assert sol.newton_steps[b] == ref["newton_steps"] and sol.outer_iters[b] == ref["outer_iters"]
+        np.testing.assert_allclose(sol.x[:, b], ref["x"], rtol=1e-9)
+        np.testing.assert_allclose(sol.y[:, b], ref["y"], rtol=1e-9)
+        assert sol.ϵ[b] == pytest.approx(ref["eps"], rel=1e-12)
+    r6 = g["readme_qp_tol1e-6"]
+    s6 = solve(InteriorPoint(), readme_mcp, np.array(r6["theta"]), tol=1e-6)
+    assert s6.outer_iters == r6["outer_iters"] and s6.newton_steps == r6["newton_steps"]
+    np.testing.assert_allclose(s6.x, r6["x"], rtol=1e-9)
+    gc = g["clamp_game"]
+    sc = solve(InteriorPoint(), clamp_game.mcp, np.array(gc["theta"]), tol=gc["tol"])
+    assert sc.status == gc["status"] and sc.newton_steps == gc["newton_steps"]
+    np.testing.assert_allclose(sc.x, gc["x"], rtol=1e-7, atol=1e-12)
+    # golden sensitivities of the README QP
+    from mcp_b200 import solve_jacobian_θ
+    gd = g["readme_qp_default"]
+    sd = solve(InteriorPoint(), readme_mcp, np.array(gd["theta"]))
+    np.testing.assert_allclose(solve_jacobian_θ(readme_mcp, sd, np.array(gd["theta"])), gd["dzdtheta"],
+                               rtol=SENS_TOL, atol=1e-9)
+
+
+# ---- cfg2: random convex QP (benchmark/quadratic_program_benchmark.jl) -------------------------------------
+def test_random_qp_100x100():
+    """The benchmark's own size: 100 primals, 100 inequalities, θ = [vec(M); vec(A); b; ϕ] (20 200 entries),
+    dense condensed system; cold start and the warm-started θ sweep of SURVEY.md §8d."""
+    mcp = problems.random_qp(100, 100)
+    Θ = problems.random_qp_thetas(12, seed=1)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    from oracle import c_oracle as CO
+    ref = CO.solve_batch(mcp.ir, Θ, tol=1e-6)
+    np.testing.assert_array_equal(sol.status, ref.status)
+    ok = sol.status == 0
+    assert ok.sum() >= 6
+    assert np.all(np.abs(sol.newton_steps[ok] - ref.newton_steps[ok]) <= 1)
+    for b in np.nonzero(ok)[0]:
+        assert rel_err(sol.x[:, b], ref.x[:, b]) <= RTOL and rel_err(sol.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
+    # θ sweep: perturb ϕ, warm start from the previous solution (y₀ clamped away from zero)
+    rng = np.random.default_rng(5)
+    Θ2 = Θ.copy()
+    Θ2[-100:] += 0.01 * rng.standard_normal((100, Θ.shape[1]))
+    x0, y0 = sol.x.copy(), np.maximum(sol.y, 1e-3)
+    warm = solve(InteriorPoint(), mcp, Θ2, x0=x0, y0=y0, tol=1e-6)
+    refw = CO.solve_batch(mcp.ir, Θ2, x0=x0, y0=y0, tol=1e-6)
+    np.testing.assert_array_equal(warm.status, refw.status)
+    for b in np.nonzero(warm.status == 0)[0]:
+        assert abs(int(warm.newton_steps[b]) - int(refw.newton_steps[b])) <= 1
+        assert rel_err(warm.x[:, b], refw.x[:, b]) <= RTOL
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------------------
+def test_empty_and_single_batches(readme_mcp):
+    empty = solve(InteriorPoint(), readme_mcp, np.zeros((2, 0)))
+    assert empty.x.shape == (2, 0) and empty.status.shape == (0,)
+    one = solve(InteriorPoint(), readme_mcp, np.array([[0.3], [0.7]]))
+    ref = O.solve_interior_point(OracleMCP(readme_mcp.ir), [0.3, 0.7])
+    np.testing.assert_allclose(one.x[:, 0], ref.x, rtol=1e-9)
+
+
+def test_ragged_batch_sizes(readme_mcp):
+    """Batch sizes that are not multiples of the warp / CTA / grid size must all be covered exactly once."""
+    om = OracleMCP(readme_mcp.ir)
+    for B in (1, 31, 33, 2369, 2371):
+        Θ = problems.readme_qp_thetas(B, seed=B)
+        sol = solve(InteriorPoint(), readme_mcp, Θ)
+        assert np.all(sol.status == 0) and np.all(sol.newton_steps > 0)
+        for b in (0, B // 2, B - 1):
+            np.testing.assert_allclose(sol.x[:, b], O.solve_interior_point(om, Θ[:, b]).x, rtol=1e-9)
+
+
+def test_initial_point_kwargs_and_in_place(readme_mcp):
+    """x₀, y₀, s₀ all given (src/solver.jl:39-41); outputs may alias them like the reference's x = x₀ (:64-66)."""
+    om = OracleMCP(readme_mcp.ir)
+    rng = np.random.default_rng(0)
+    B = 40
+    Θ = problems.readme_qp_thetas(B, seed=9)
+    x0, y0, s0 = rng.normal(size=(2, B)), rng.random((2, B)) + 0.1, rng.random((2, B)) + 0.1
+    sol = solve(InteriorPoint(), readme_mcp, Θ, x0=x0, y0=y0, s0=s0)
+    for b in range(B):
+        ref = O.solve_interior_point(om, Θ[:, b], x0=x0[:, b], y0=y0[:, b], s0=s0[:, b])
+        assert (ref.status == "solved") == (sol.status[b] == 0)
+        if ref.status == "solved":
+            assert abs(ref.newton_steps - int(sol.newton_steps[b])) <= 1
+            assert rel_err(sol.x[:, b], ref.x) <= RTOL and rel_err(sol.y[:, b], ref.y) <= RTOL
+
+
+def test_option_passthrough(readme_mcp):
+    """tol, iteration caps, rates and min_stepsize reach the kernel (src/solver.jl:42-49)."""
+    om = OracleMCP(readme_mcp.ir)
+    θ = np.array([-0.5, 0.5])
+    for kw in (dict(max_outer_iters=3), dict(max_inner_iters=3), dict(tightening_rate=0.3, loosening_rate=0.2),
+               dict(tol=1e-8), dict(min_stepsize=0.6)):
+        ref = O.solve_interior_point(om, θ, **kw)
+        sol = solve(InteriorPoint(), readme_mcp, θ, **kw)
+        assert sol.status == ref.status and sol.outer_iters == ref.outer_iters and sol.newton_steps == ref.newton_steps, kw
+        np.testing.assert_allclose(sol.x, ref.x, rtol=1e-8)
+        assert sol.ϵ == pytest.approx(ref.eps, rel=1e-10)
+
+
+def test_infeasible_and_nan_instances(lane_game):
+    """A colliding start is infeasible ⇒ :failed at the outer cap; a NaN θ must not hang or poison neighbours."""
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(4, seed=1)
+    Θ[:, 1] = [1.0, 10.0, 0, 0, 1.0, 1.2, 10.1, 0, 0, 3.0]
+    Θ[0, 2] = np.nan
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    assert sol.status[1] == 1 and sol.outer_iters[1] == 50
+    om = OracleMCP(mcp.ir)
+    for b in (0, 3):                       # the neighbours of the NaN instance are unaffected
+        ref = O.solve_interior_point(om, Θ[:, b], tol=1e-6)
+        assert (ref.status == "solved") == (sol.status[b] == 0)
+        if ref.status == "solved":
+            assert rel_err(sol.x[:, b], ref.x) <= RTOL
+
+
+def test_large_batch_properties(lane_game):
+    """At bench scale the oracle is too slow to run in full: check size-independent properties — every
+    instance written exactly once, converged instances satisfy the KKT residual bound they claim, and a
+    sample agrees with the C oracle."""
+    from oracle import c_oracle as CO
+    mcp = lane_game.mcp
+    B = 20000
+    Θ = problems.lane_change_thetas(B, seed=123)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    assert np.all((sol.status == 0) | (sol.status == 1)) and np.all(sol.outer_iters >= 2)
+    ok = sol.status == 0
+    assert 0.9 < ok.mean() < 0.99
+    assert np.all(np.isfinite(sol.x[:, ok])) and np.all(sol.y[:, ok] > 0) and np.all(sol.s[:, ok] > 0)
+    assert np.all((sol.kkt_error[ok] <= 1e-6) | (sol.ϵ[ok] <= 1e-6))     # the loop's own exit test (:71)
+    assert np.max(sol.s[:, ok] * sol.y[:, ok]) < 1e-2                     # complementarity at the ϵ scale
+    idx = np.random.default_rng(0).choice(B, 64, replace=False)
+    ref = CO.solve_batch(mcp.ir, Θ[:, idx], tol=1e-6)
+    agree = 0
+    for k, b in enumerate(idx):
+        if ref.status[k] == 0 and sol.status[b] == 0 and abs(int(ref.newton_steps[k]) - int(sol.newton_steps[b])) <= 1 \
+                and rel_err(sol.x[:, b], ref.x[:, k]) <= RTOL:
+            agree += 1
+        elif ref.status[k] == 1 and sol.status[b] == 1:
+            agree += 1
+    assert agree >= 62
