@@ -115,10 +115,19 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(mcp, Θ, sample: int, threads: int = 0):
     """The reference algorithm (C restatement, oracle/c) on the host cores, on the first `sample` θ."""
     from oracle import c_oracle as CO
     CO.build()
+    threads = threads or host_threads()
     Θs = np.asfortranarray(Θ[:, :sample])
     CO.solve_batch(mcp.ir, Θs[:, :8], tol=TOL, nthreads=threads)      # warm-up (column ordering, page-in)
     t0 = time.perf_counter()
@@ -140,13 +149,13 @@ def run_reference(args):
     Θ = gen(sample, 1)
     from oracle import c_oracle as CO
     CO.build()
-    threads = CO.max_threads()
+    threads = host_threads()
     for _ in range(args.warmup):
-        CO.solve_batch(mcp.ir, Θ[:, :min(sample, 64)], tol=TOL)
+        CO.solve_batch(mcp.ir, Θ[:, :min(sample, 64)], tol=TOL, nthreads=threads)
     t0 = time.perf_counter()
     solved = 0
     for _ in range(args.steps):
-        r = CO.solve_batch(mcp.ir, Θ, tol=TOL)
+        r = CO.solve_batch(mcp.ir, Θ, tol=TOL, nthreads=threads)
         solved += int((r.status == 0).sum())
     dt = time.perf_counter() - t0
     v = solved / dt
