@@ -4,7 +4,8 @@
 // assembly tables as __device__ const arrays, and the device functions mcp_eval_newton_par / mcp_eval_sens_par
 // lowered from the traced G, H and Jacobian entries) and hands the result to NVRTC for sm_100a.
 //
-// One WARP owns one problem instance for its whole solve (persistent over Newton iterations): the
+// One SUB-WARP (SUB = 16 lanes when the factorisation window has ≤ 16 rows, else the full warp) owns one
+// problem instance for its whole solve (persistent over Newton iterations): the
 // iterate (x, y, s), residuals, Jacobian entries and the active window of the banded factorisation live
 // in shared memory; HBM is touched for θ/x₀/y₀/s₀ in, (x, y, s, …) out, and an L2-resident scratch that
 // streams the banded condensed matrix into the window and the finished U rows out of it.
@@ -16,9 +17,9 @@
 //   IFT sensitivities                   src/AutoDiff.jl:18-40,59-76,98
 //
 // Macros provided by the prologue:
-//   NX NY NT NRED KL KU WC WR WS1 WSS NRHS_SENS NJV NJTV ND THETA_IN_SMEM
-//   SOLVE_WARPS SENS_WARPS  SOLVE_SMEM_DOUBLES SENS_SMEM_DOUBLES (per warp)  SHARED_TABLE_DOUBLES (per CTA)
-//   SOLVE_SCRATCH SENS_SCRATCH CVAL_DOUBLES (doubles per warp)  HAS_JT
+//   NX NY NT NRED KL KU WC WR WS1 WSS NRHS_SENS NJV NJTV ND THETA_IN_SMEM SUB
+//   SOLVE_INST SENS_INST (instances per CTA)  SOLVE_SMEM_DOUBLES SENS_SMEM_DOUBLES (per instance)
+//   SHARED_TABLE_DOUBLES (per CTA)  SOLVE_SCRATCH SENS_SCRATCH CVAL_DOUBLES (doubles per instance)  HAS_JT
 // Tables: D_ROWPTR D_CPOS D_TP (dests), T_COEF T_I (terms), R_GROW R_PTR R_CODE R_K R_COEF (rhs),
 //   H_PTR H_CODE H_COL H_COEF (H_x rows), PERM, Q_PTR Q_ROW Q_CODE Q_COEF (θ-Jacobian by column)
 
@@ -72,18 +73,23 @@ __device__ __forceinline__ double opval(int code, const double* __restrict__ jv,
   return code >= 0 ? jv[code] : (code == -1 ? 1.0 : th[-2 - code]);
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
+// lanes of my sub-warp (the whole warp when SUB == 32)
+__device__ __forceinline__ unsigned sub_mask(int lane) {
+  return (SUB == 32) ? FULLMASK : (0xffffu << (lane & 16));
+}
+
+__device__ __forceinline__ double sub_sum(double v, unsigned smask) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  for (int o = SUB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(smask, v, o, SUB);
   return v;
 }
 
 // NaN-propagating max, like Julia's norm(F, Inf) (src/solver.jl:107)
 __device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
 
-__device__ __forceinline__ double warp_nanmax(double v) {
+__device__ __forceinline__ double sub_nanmax(double v, unsigned smask) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULLMASK, v, o));
+  for (int o = SUB / 2; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(smask, v, o, SUB));
   return v;
 }
 
