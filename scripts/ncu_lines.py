@@ -13,6 +13,7 @@ agg = collections.OrderedDict()
 cur_line, cur_src = None, ""
 for r in rows[hi + 1:]:
     if len(r) < len(hdr): continue
+    if r[0] == 'Line No': break   # a second kernel in the same report
     if r[0]: cur_line, cur_src = int(r[0]), r[1]
     if not r[2]: continue
     a = agg.setdefault(cur_line, [0, 0, cur_src, collections.Counter()])
