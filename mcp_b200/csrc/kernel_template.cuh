@@ -24,6 +24,10 @@
 //   H_PTR H_CODE H_COL H_COEF (H_x rows), PERM, Q_PTR Q_ROW Q_CODE Q_COEF (θ-Jacobian by column)
 
 #define FULLMASK 0xffffffffu
+#ifndef SUB
+#define SUB 32  // lanes per instance
+#endif
+#define DBL_MAX_ 1.7976931348623157e308
 
 struct SolveParams {
   long long B;
@@ -84,6 +88,8 @@ __device__ __forceinline__ double sub_sum(double v, unsigned smask) {
   return v;
 }
 
+__device__ __forceinline__ double warp_sum(double v) { return sub_sum(v, FULLMASK); }
+
 // NaN-propagating max, like Julia's norm(F, Inf) (src/solver.jl:107)
 __device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
 
@@ -92,6 +98,8 @@ __device__ __forceinline__ double sub_nanmax(double v, unsigned smask) {
   for (int o = SUB / 2; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(smask, v, o, SUB));
   return v;
 }
+
+__device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, FULLMASK); }
 
 // ------------------------------------------------------------------------------------------------
 // CTA-shared tables (first SHARED_TABLE_DOUBLES doubles of dynamic shared memory): ROWPTR_S[NRED+1]
@@ -111,28 +119,28 @@ __device__ __forceinline__ void load_shared_tables(double* smem_base) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, double* __restrict__ tmp,
                                                 const double* __restrict__ jv, const double* __restrict__ th,
-                                                const double* __restrict__ dinv, double tol, int lane) {
+                                                const double* __restrict__ dinv, double tol, int sl, unsigned smask) {
   // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
 #if ASM_TWO_PHASE
   // phase A, term-parallel (all table loads independent and coalesced): tmp[t] = coef·val(a)·[D⁻¹_k·val(b)]
-  for (int t = lane; t < NTERMS; t += 32) {
+  for (int t = sl; t < NTERMS; t += SUB) {
     const int4 ti = T_I[t];  // {a, b, k, -}
     double v = T_COEF[t] * opval(ti.x, jv, th);
     if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
     tmp[t] = v;
   }
-  __syncwarp();
+  __syncwarp(smask);
   // phase B, dest-parallel: sum the (contiguous) terms of each dest
-  for (int d = lane; d < ND; d += 32) {
+  for (int d = sl; d < ND; d += SUB) {
     const int tp = D_TP[d];
     const int t1 = D_TP[d + 1] & 0x7fffffff;
     double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
     for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t];
-    Cval[d] = acc;
+    __stcg(Cval + d, acc);   // streaming scratch: keep L1 for the assembly tables
   }
-  __syncwarp();
+  __syncwarp(smask);
 #else
-  for (int d = lane; d < ND; d += 32) {
+  for (int d = sl; d < ND; d += SUB) {
     const int tp = D_TP[d];
     const int t1 = D_TP[d + 1] & 0x7fffffff;
     double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
@@ -142,14 +150,14 @@ __device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, doubl
       if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
       acc += v;
     }
-    Cval[d] = acc;
+    __stcg(Cval + d, acc);
   }
 #endif
 }
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");  // L2 only
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -165,7 +173,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //          swapped: the pivot's slot is retired and re-used by the row entering the window, so partial
 //          pivoting moves no data.
 //   Cval : global, the assembled non-zeros (row-sorted); rows are scattered into the window as they enter.
-//   UT   : global scratch, NRED × WC: U stored TRANSPOSED, UT[c*WC + (c-i)] = U[i][c], with the
+//   UT   : global scratch, NRED × UTS (UTS = WC rounded up to even): U stored TRANSPOSED, UT[c*UTS + (c-i)] = U[i][c], with the
 //          reciprocal pivot at offset 0, so that the back substitution reads one contiguous row per
 //          column and needs no warp reduction.
 //   sol  : shared, NRHS × NRED: right-hand sides on entry, solution on exit (permuted ordering).
@@ -177,19 +185,119 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int NRHS, int WS>
 __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cval, double* __restrict__ UT,
                           double* __restrict__ sol, const int* __restrict__ rowptr,
-                          const unsigned short* __restrict__ cpos, int lane) {
-  constexpr int CPW = (WC + 31) / 32;  // matrix positions per lane
-  constexpr int RPL = (WR + 31) / 32;  // row slots per lane
-  constexpr int WPL = (WS + 31) / 32;
+                          const unsigned short* __restrict__ cpos, int sl, unsigned smask) {
+  constexpr int CPW = (WC + SUB - 1) / SUB;  // matrix positions per sl
+  constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
+  constexpr int WPL = (WS + SUB - 1) / SUB;
 
+  constexpr int NPOS = WC + NRHS;
+  if constexpr (REGWIN && WR <= SUB && NPOS <= 40) {
+    // ============ register-resident window ==========================================================
+    // Every sl keeps ITS window row in registers, in a layout relative to the pivot column: a[d] is the
+    // entry in column j+d (d = 0 … WC-1), a[WC+q] the q-th right-hand side.  Eliminating column j and
+    // advancing the window are one operation, a[d] ← a[d+1] − m·u[d+1]: the FMA's destination register does
+    // the shift for free, position 0 is always the pivot column, and the loop body stays small (rolled).
+    // The pivot row is broadcast with shuffles; shared memory only stages the entering row.  (Measured on
+    // the shared-memory variant below: the smem pipe sat at 60 % of peak re-loading/re-storing window rows.)
+    double a[NPOS];
+    double* E = W;  // two staging rows of WS doubles, alternating between steps
+#pragma unroll
+    for (int i = 0; i < NPOS; ++i) a[i] = 0.0;
+    for (int r = 0; r < WR; ++r) {  // rows 0 … WR-1, relative to column 0
+      for (int q = sl; q < WS; q += SUB) E[q] = 0.0;
+      __syncwarp(smask);
+      for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = __ldcg(Cval + e);  // columns < WC: no wrap yet
+      if (sl < NRHS) E[WC + sl] = sol[sl * NRED + r];
+      __syncwarp(smask);
+      if (sl == r) {
+#pragma unroll
+        for (int i = 0; i < NPOS; ++i) a[i] = E[i];
+      }
+      __syncwarp(smask);
+    }
+    int cj1 = (1 == WC) ? 0 : 1;  // (j+1) % WC: circular position of the column that becomes d = 0 next
+#pragma unroll 1
+    for (int j = 0; j < NRED; ++j) {
+      double* Eb = E + (j & 1) * WS;
+      const int ienter = j + WR;
+      int e0 = 0, e1 = 0;
+      if (ienter < NRED) {
+        e0 = rowptr[ienter];
+        e1 = rowptr[ienter + 1];
+      }
+      double pre[CPW];
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int e = e0 + sl + SUB * k;
+        pre[k] = (e < e1) ? __ldcg(Cval + e) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const int q = sl + SUB * k;
+        if (q < WS) Eb[q] = 0.0;
+      }
+      // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, row in the low byte ----
+      unsigned key = 0;
+      if (sl < WR) key = ((unsigned)__double2hiint(fabs(a[0])) & 0xffffff00u) | (unsigned)(255 - sl);
+      const unsigned best = __reduce_max_sync(smask, key);
+      const int p = 255 - (int)(best & 0xffu);
+      const double piv = __shfl_sync(smask, a[0], p, SUB);
+      if (!(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) return 1;  // zero, NaN or Inf pivot
+      const double rp = 1.0 / piv;
+      const double m = (sl < WR && sl != p) ? -(a[0] * rp) : 0.0;
+      // ---- retire the pivot row: its owner writes U row j out transposed, its RHS into sol -------------
+      if (sl == p) {
+        const int tmax = min(WC - 1, NRED - 1 - j);
+        double* Uj = UT + (size_t)j * UTS;
+        __stcg(Uj, rp);
+#pragma unroll
+        for (int d = 1; d < WC; ++d)
+          if (d <= tmax) __stcg(Uj + d * (UTS + 1), a[d]);
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) sol[q * NRED + j] = a[WC + q];
+      }
+      // ---- eliminate column j and slide the window: a[d] ← a[d+1] − m·u[d+1] --------------------------------
+#pragma unroll
+      for (int d = 0; d + 1 < WC; ++d) {
+        const double u = __shfl_sync(smask, a[d + 1], p, SUB);
+        a[d] = fma(m, u, a[d + 1]);
+      }
+      a[WC - 1] = 0.0;  // column j+WC enters the window (structurally zero in every resident row)
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) {
+        const double u = __shfl_sync(smask, a[WC + q], p, SUB);
+        a[WC + q] = fma(m, u, a[WC + q]);
+      }
+      // ---- the entering row (relative to column j+1) takes over the retired sl ----------------------------
+      __syncwarp(smask);
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int e = e0 + sl + SUB * k;
+        if (e < e1) {
+          int d = (int)cpos[e] - cj1;
+          if (d < 0) d += WC;
+          Eb[d] = pre[k];
+        }
+      }
+      if (sl < NRHS && ienter < NRED) Eb[WC + sl] = sol[sl * NRED + ienter];
+      __syncwarp(smask);
+      if (sl == p) {
+#pragma unroll
+        for (int i = 0; i < NPOS; ++i) a[i] = Eb[i];
+      }
+      cj1 = (cj1 + 1 == WC) ? 0 : cj1 + 1;
+    }
+    __syncwarp(smask);
+  } else {
+  // ============ shared-memory window (any size) =====================================================
   // ---- initial window: rows 0 … WR-1 -----------------------------------------------------------
-  for (int i = lane; i < WR * WS; i += 32) W[i] = 0.0;
-  __syncwarp();
+  for (int i = sl; i < WR * WS; i += SUB) W[i] = 0.0;
+  __syncwarp(smask);
   for (int r = 0; r < WR; ++r) {
-    for (int e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) W[r * WS + cpos[e]] = Cval[e];
-    if (lane < NRHS) W[r * WS + WC + lane] = sol[lane * NRED + r];
+    for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) W[r * WS + cpos[e]] = __ldcg(Cval + e);
+    if (sl < NRHS) W[r * WS + WC + sl] = sol[sl * NRED + r];
   }
-  __syncwarp();
+  __syncwarp(smask);
 
   constexpr int NP = (WC + NRHS + 1) / 2;  // position pairs swept per row (matrix + rhs columns)
   constexpr int PB = (NP < 9) ? NP : 9;    // pairs per register batch
@@ -207,7 +315,7 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
     double pre[CPW];
 #pragma unroll
     for (int k = 0; k < CPW; ++k) {
-      const int e = e0 + lane + 32 * k;
+      const int e = e0 + sl + SUB * k;
       pre[k] = (e < e1) ? Cval[e] : 0.0;
     }
 
@@ -216,51 +324,51 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
     double m[RPL];
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-      const int r = lane + 32 * k;
+      const int r = sl + SUB * k;
       m[k] = (r < WR) ? W[r * WS + cj] : 0.0;
       if (r < WR) {
         const unsigned key = ((unsigned)__double2hiint(fabs(m[k])) & 0xffffff00u) | (unsigned)(255 - r);
         best = max(best, key);
       }
     }
-    best = __reduce_max_sync(FULLMASK, best);
+    best = __reduce_max_sync(smask, best);
     const int p = 255 - (int)(best & 0xffu);
     double piv = m[0];
 #pragma unroll
     for (int k = 1; k < RPL; ++k)
-      if ((p >> 5) == k) piv = m[k];
-    piv = __shfl_sync(FULLMASK, piv, p & 31);
-    if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1.0e300 * 1.0e300)) return 1;  // zero, NaN or Inf pivot
+      if ((p / SUB) == k) piv = m[k];
+    piv = __shfl_sync(smask, piv, p % SUB, SUB);
+    if (!(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) return 1;  // zero, NaN or Inf pivot
     const double rp = 1.0 / piv;
     double* Wp = W + p * WS;
     // Invariant: every entry of a window row outside its structural extent is exactly zero, so the
     // update can sweep ALL positions with static code; only the pivot's own position must read as zero.
-    if (lane == 0) Wp[cj] = 0.0;
-    __syncwarp();
+    if (sl == 0) Wp[cj] = 0.0;
+    __syncwarp(smask);
 
     // ---- retire the pivot row: U row j goes out transposed, its RHS into sol ------------------------
     {
       const int tmax = min(WC - 1, NRED - 1 - j);
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
-        const int q = lane + 32 * k;
+        const int q = sl + SUB * k;
         if (q < WC) {
           int d = q - cj;
           if (d < 0) d += WC;
-          if (d <= tmax) UT[(j + d) * WC + d] = (d == 0) ? rp : Wp[q];
+          if (d <= tmax) __stcg(UT + (size_t)(j + d) * UTS + d, (d == 0) ? rp : Wp[q]);
         }
       }
-      if (lane < NRHS) sol[lane * NRED + j] = Wp[WC + lane];
+      if (sl < NRHS) sol[sl * NRED + j] = Wp[WC + sl];
     }
 
     // ---- eliminate column j: every row (lanes own rows) minus multiplier × pivot row -----------------
     // Rows with a zero multiplier (and the pivot row itself, whose multiplier is forced to zero) are
-    // rewritten unchanged: no per-lane branches, 128-bit conflict-free accesses (WS ≡ 2 mod 4).
+    // rewritten unchanged: no per-sl branches, 128-bit conflict-free accesses (WS ≡ 2 mod 4).
     {
       const double2* Wp2 = reinterpret_cast<const double2*>(Wp);
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
-        const int r = lane + 32 * k;
+        const int r = sl + SUB * k;
         m[k] = (r < WR && r != p) ? -(m[k] * rp) : 0.0;
       }
 #pragma unroll
@@ -271,7 +379,7 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
           if (b0 + i < NP) u[i] = Wp2[b0 + i];
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
-          const int r = lane + 32 * k;
+          const int r = sl + SUB * k;
           if (r < WR) {
             double2* Wr2 = reinterpret_cast<double2*>(W + r * WS);
             double2 a[PB];
@@ -290,29 +398,31 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
       }
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
-        const int r = lane + 32 * k;
+        const int r = sl + SUB * k;
         if (r < WR && r != p) W[r * WS + cj] = 0.0;  // the eliminated entry (exactly zero by construction)
       }
     }
-    __syncwarp();
+    __syncwarp(smask);
 
     // ---- the entering row takes the retired slot ---------------------------------------------------
     {
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
-        const int q = lane + 32 * k;
+        const int q = sl + SUB * k;
         if (q < WS) Wp[q] = 0.0;
       }
-      __syncwarp();
+      __syncwarp(smask);
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
-        const int e = e0 + lane + 32 * k;
+        const int e = e0 + sl + SUB * k;
         if (e < e1) Wp[cpos[e]] = pre[k];
       }
-      if (lane < NRHS && ienter < NRED) Wp[WC + lane] = sol[lane * NRED + ienter];
+      if (sl < NRHS && ienter < NRED) Wp[WC + sl] = sol[sl * NRED + ienter];
     }
-    __syncwarp();
+    __syncwarp(smask);
     cj = (cj + 1 == WC) ? 0 : cj + 1;
+  }
+
   }
 
   // ---- back substitution: column sweep, x_j = rhs_j / u_jj then rhs_i −= U[i][j] x_j for i < j.
@@ -322,47 +432,47 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
     double* ring = W;
     auto issue = [&](int col) {
       if (col >= 0) {
-        const double* src = UT + (size_t)col * WC;
-        double* dst = ring + ((NRED - 1 - col) % RING_D) * WC;
+        const double* src = UT + (size_t)col * UTS;
+        double* dst = ring + ((NRED - 1 - col) % RING_D) * UTS;
 #pragma unroll
-        for (int k = 0; k < CPW; ++k) {
-          const int t = lane + 32 * k;
-          if (t < WC) cp_async8(dst + t, src + t);
+        for (int k = 0; k < (UTS / 2 + SUB - 1) / SUB; ++k) {
+          const int t2 = sl + SUB * k;  // pair index
+          if (t2 < UTS / 2) cp_async16(dst + 2 * t2, src + 2 * t2);
         }
       }
       cp_async_commit();  // (possibly empty) group: keeps the group count uniform
     };
-    __syncwarp();
+    __syncwarp(smask);
 #pragma unroll 1
     for (int i = 0; i < RING_D - 1; ++i) issue(NRED - 1 - i);
 #pragma unroll 1
     for (int j = NRED - 1; j >= 0; --j) {
       issue(j - (RING_D - 1));
       cp_async_wait<RING_D - 1>();
-      __syncwarp();
-      const double* Uj = ring + ((NRED - 1 - j) % RING_D) * WC;
+      __syncwarp(smask);
+      const double* Uj = ring + ((NRED - 1 - j) % RING_D) * UTS;
       const double rd = Uj[0];
       double ut[CPW];
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
-        const int t = lane + 1 + 32 * k;
+        const int t = sl + 1 + SUB * k;
         ut[k] = (t < WC) ? Uj[t] : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < NRHS; ++q) {
         double xj = 0.0;
-        if (lane == 0) {
+        if (sl == 0) {
           xj = sol[q * NRED + j] * rd;
           sol[q * NRED + j] = xj;
         }
-        xj = __shfl_sync(FULLMASK, xj, 0);
+        xj = __shfl_sync(smask, xj, 0, SUB);
 #pragma unroll
         for (int k = 0; k < CPW; ++k) {
-          const int t = lane + 1 + 32 * k;
+          const int t = sl + 1 + SUB * k;
           if (t < WC && t <= j) sol[q * NRED + j - t] = fma(-ut[k], xj, sol[q * NRED + j - t]);
         }
       }
-      __syncwarp();
+      __syncwarp(smask);
     }
   }
   return 0;
@@ -370,13 +480,13 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
 
 // `fraction_to_the_boundary_linesearch` — src/solver.jl:127-138, literally (τ = 0.995, decay = 0.5).
 __device__ __forceinline__ double ftb_linesearch(const double* __restrict__ v, const double* __restrict__ d,
-                                                 double min_step, int lane) {
+                                                 double min_step, int sl, unsigned smask) {
   const double c = 1.0 - 0.995;
   double alpha = 1.0;
   for (int it = 0; it < 1200; ++it) {
     bool viol = false;
-    for (int k = lane; k < NY; k += 32) viol = viol || (v[k] + alpha * d[k] < c * v[k]);  // :129
-    if (!__any_sync(FULLMASK, viol)) return alpha;
+    for (int k = sl; k < NY; k += SUB) viol = viol || (v[k] + alpha * d[k] < c * v[k]);  // :129
+    if (!__any_sync(smask, viol)) return alpha;
     if (alpha < min_step) break;  // :130 — tested before halving
     alpha *= 0.5;                 // :134
   }
@@ -384,16 +494,20 @@ __device__ __forceinline__ double ftb_linesearch(const double* __restrict__ v, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// The solve kernel: persistent warps pull instances from a global queue.
+// The solve kernel: persistent CTAs; every sub-warp (SUB lanes) pulls instances from a global queue and
+// runs the reference's loop (src/solver.jl:63-121) as a small state machine, one Newton step per trip
+// of the main loop.  The sub-warps of a warp re-align once per Newton step (the full-warp vote below),
+// so the heavy phases of their two instances execute as the same instructions.
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kernel(const SolveParams p) {
+extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kernel(const SolveParams p) {
   extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int sl = threadIdx.x % SUB;
+  const int slot = threadIdx.x / SUB;  // instance slot of this sub-warp within the CTA
+  const unsigned smask = sub_mask(threadIdx.x & 31);
   load_shared_tables(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
-  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)warp * SOLVE_SMEM_DOUBLES;
+  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SOLVE_SMEM_DOUBLES;
   double* x = S + SOLVE_OFF_X;
   double* y = S + SOLVE_OFF_Y;
   double* s = S + SOLVE_OFF_S;
@@ -406,8 +520,10 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
   double* W = S + SOLVE_OFF_WIN;
 #if THETA_IN_SMEM
   double* th = S + SOLVE_OFF_TH;
+#else
+  const double* th = p.theta;
 #endif
-  double* Cval = p.scratch + ((size_t)blockIdx.x * SOLVE_WARPS + warp) * SOLVE_SCRATCH;
+  double* Cval = p.scratch + ((size_t)blockIdx.x * SOLVE_INST + slot) * SOLVE_SCRATCH;
   double* UT = Cval + CVAL_DOUBLES;
   const double tol = p.tol;
 
@@ -417,135 +533,167 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
   // boundaries, where the whole solver state is (x, y, s, ϵ, kkt_error, outer_iters)), parks the rest in
   // the output arrays and a deferred list; pass 1 (a second launch) resumes them, all long, together.
   const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+
+  // solver state of my sub-warp's instance (replicated in each of its lanes)
+  bool have = false, done = false, head = true, brk = false;
+  unsigned long long inst = 0;
+  double eps = 1.0, kkt = 0.0;
+  int status = 0, outer = 1, inner = 1, steps = 0;
+
   for (;;) {
-    unsigned long long inst = 0;
-    if (lane == 0) inst = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
-    inst = __shfl_sync(FULLMASK, inst, 0);
-    if (p.pass) {
-      if (inst >= n_deferred) break;
-      inst = (unsigned long long)p.deferred[inst];
-    } else if (inst >= (unsigned long long)p.B) {
-      break;
-    }
-
-    // ---- load θ and the initial point (src/solver.jl:39-41,64-66) — or the parked state in pass 1 ----
+    // ---- control: advance my instance to its next Newton step (or fetch another, or run dry) -------------
+    bool step = false;
+    while (!done && !step) {
+      if (!have) {
+        unsigned long long q = 0;
+        if (sl == 0) q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+        q = __shfl_sync(smask, q, 0, SUB);
+        if (p.pass) {
+          if (q >= n_deferred) {
+            done = true;
+            break;
+          }
+          inst = (unsigned long long)p.deferred[q];
+        } else {
+          if (q >= (unsigned long long)p.B) {
+            done = true;
+            break;
+          }
+          inst = q;
+        }
+        // load θ and the initial point (src/solver.jl:39-41,64-66) — or the parked state in pass 1
 #if THETA_IN_SMEM
-    for (int i = lane; i < NT; i += 32) th[i] = p.theta[inst * NT + i];
+        for (int i = sl; i < NT; i += SUB) th[i] = p.theta[inst * NT + i];
 #else
-    const double* th = p.theta + inst * NT;
+        th = p.theta + inst * NT;
 #endif
-    double eps = 1.0;                                        // :67
-    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // Inf, :68
-    int status = 0;                                          // :69
-    int outer = 1;                                           // :70
-    int steps = 0;
-    if (p.pass) {
-      for (int i = lane; i < NX; i += 32) x[i] = p.x_out[inst * NX + i];
-      for (int i = lane; i < NY; i += 32) {
-        y[i] = p.y_out[inst * NY + i];
-        s[i] = p.s_out[inst * NY + i];
+        eps = 1.0;                                         // :67
+        kkt = __longlong_as_double(0x7ff0000000000000LL);  // Inf, :68
+        status = 0;                                        // :69
+        outer = 1;                                         // :70
+        steps = 0;
+        if (p.pass) {
+          for (int i = sl; i < NX; i += SUB) x[i] = p.x_out[inst * NX + i];
+          for (int i = sl; i < NY; i += SUB) {
+            y[i] = p.y_out[inst * NY + i];
+            s[i] = p.s_out[inst * NY + i];
+          }
+          eps = p.eps_out[inst];
+          kkt = p.kkt_out[inst];
+          outer = p.outer_out[inst];
+          steps = p.steps_out[inst];
+        } else {
+          for (int i = sl; i < NX; i += SUB) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+          for (int i = sl; i < NY; i += SUB) {
+            y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+            s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+          }
+        }
+        __syncwarp(smask);
+        have = true;
+        head = true;
+        brk = false;
       }
-      eps = p.eps_out[inst];
-      kkt = p.kkt_out[inst];
-      outer = p.outer_out[inst];
-      steps = p.steps_out[inst];
+      if (head) {  // top of the outer (ϵ-homotopy) loop, :71
+        const bool go = kkt > tol && eps > tol && outer < p.max_outer;
+        const bool park = go && p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget;
+        if (!go || park) {
+          if (!park && outer == p.max_outer) status = 1;  // :117-119
+          for (int i = sl; i < NX; i += SUB) p.x_out[inst * NX + i] = x[i];
+          for (int i = sl; i < NY; i += SUB) {
+            p.y_out[inst * NY + i] = y[i];
+            p.s_out[inst * NY + i] = s[i];
+          }
+          if (sl == 0) {
+            p.kkt_out[inst] = kkt;
+            p.eps_out[inst] = eps;
+            p.outer_out[inst] = outer;
+            p.status_out[inst] = status;
+            p.steps_out[inst] = steps;
+            if (park) {
+              p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+            } else {
+              atomicAdd(p.counters + 1, (unsigned long long)steps);
+              if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+            }
+          }
+          __syncwarp(smask);
+          have = false;
+          continue;
+        }
+        inner = 1;   // :72
+        status = 0;  // :73
+        head = false;
+      }
+      if (!brk && kkt > eps && inner < p.max_inner) {  // :75
+        step = true;
+      } else {  // the inner loop is over: ϵ update, :111-114
+        eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);
+        ++outer;
+        head = true;
+        brk = false;
+      }
+    }
+    if (__all_sync(FULLMASK, done)) break;  // also re-aligns the warp's sub-warps once per Newton step
+    if (!step) continue;
+
+    // ---- one Newton step (src/solver.jl:76-108) -------------------------------------------------------------
+    // F and the Jacobian entries at the current iterate (:79-80); lane i evaluates output group i
+    mcp_eval_newton_par(sl, x, y, th, g, hh, jv);
+    __syncwarp(smask);
+    double fmax_ = 0.0;
+    for (int i = sl; i < NX; i += SUB) fmax_ = nanmax(fmax_, fabs(g[i]));
+    for (int k = sl; k < NY; k += SUB) {
+      const double f2 = hh[k] - s[k];             // H − s        (src/mcp.jl:78)
+      const double f3 = s[k] * y[k] - eps;        // s∘y − ϵ      (src/mcp.jl:79)
+      const double yt = y[k] + tol;               // (3,3) block diag(y) + tol·I  (:81)
+      const double di = 1.0 / (tol + s[k] / yt);  // D⁻¹, D = (2,2) block tol·I + S (Y+tol)⁻¹
+      dinv[k] = di;
+      w[k] = di * (-f2 - f3 / yt);
+      fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+    }
+    const double kkt_new = sub_nanmax(fmax_, smask);  // ‖F‖∞ of the pre-step residual (:107)
+    __syncwarp(smask);
+    // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
+    for (int i = sl; i < NRED; i += SUB) {
+      double r = -g[R_GROW[i]];
+      for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
+      sol[i] = r;
+    }
+    __syncwarp(smask);  // G (aliased onto the window) is dead from here on: the window becomes scratch
+    assemble_matrix(Cval, W, jv, th, dinv, tol, sl, smask);
+    __syncwarp(smask);
+    bool failed = band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, sl, smask) != 0;  // :84-88
+    double a_s = 1.0, a_y = 1.0;
+    if (!failed) {
+      // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
+      for (int k = sl; k < NY; k += SUB) {
+        double hx = 0.0;
+        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
+        const double dy = w[k] - dinv[k] * hx;
+        const double f3 = s[k] * y[k] - eps;
+        w[k] = dy;
+        dinv[k] = -(f3 + s[k] * dy) / (y[k] + tol);
+      }
+      __syncwarp(smask);
+      a_s = ftb_linesearch(s, dinv, p.min_stepsize, sl, smask);  // :93
+      a_y = ftb_linesearch(y, w, p.min_stepsize, sl, smask);     // :94
+      failed = (a_s != a_s) || (a_y != a_y);                     // :96-100
+    }
+    if (failed) {
+      status = 1;
+      brk = true;
     } else {
-      for (int i = lane; i < NX; i += 32) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
-      for (int i = lane; i < NY; i += 32) {
-        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
-        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      for (int c = sl; c < NRED; c += SUB) x[PERM[c]] += a_s * sol[c];  // :103 (x uses α_s)
+      for (int k = sl; k < NY; k += SUB) {
+        s[k] += a_s * dinv[k];                                          // :104
+        y[k] += a_y * w[k];                                             // :105
       }
+      kkt = kkt_new;                                                    // :107
+      ++inner;                                                          // :108
+      ++steps;
     }
-    __syncwarp();
-    bool parked = false;
-    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
-      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
-        parked = true;
-        break;
-      }
-      int inner = 1;                                         // :72
-      status = 0;                                            // :73
-      while (kkt > eps && inner < p.max_inner) {             // :75
-        // F and the Jacobian entries at the current iterate (:79-80)
-        mcp_eval_newton_par(lane, x, y, th, g, hh, jv);   // lane i evaluates output group i
-        __syncwarp();
-        double fmax_ = 0.0;
-        for (int i = lane; i < NX; i += 32) fmax_ = nanmax(fmax_, fabs(g[i]));
-        for (int k = lane; k < NY; k += 32) {
-          const double f2 = hh[k] - s[k];         // H − s        (src/mcp.jl:78)
-          const double f3 = s[k] * y[k] - eps;         // s∘y − ϵ      (src/mcp.jl:79)
-          const double yt = y[k] + tol;                // (3,3) block diag(y) + tol·I  (:81)
-          const double di = 1.0 / (tol + s[k] / yt);   // D⁻¹, D = (2,2) block tol·I + S (Y+tol)⁻¹
-          dinv[k] = di;
-          w[k] = di * (-f2 - f3 / yt);
-          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
-        }
-        const double kkt_new = warp_nanmax(fmax_);           // ‖F‖∞ of the pre-step residual (:107)
-        __syncwarp();
-
-        // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
-        for (int i = lane; i < NRED; i += 32) {
-          double r = -g[R_GROW[i]];
-          for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
-          sol[i] = r;
-        }
-        __syncwarp();   // G (aliased onto the window) is dead from here on: the window becomes scratch
-        assemble_matrix(Cval, W, jv, th, dinv, tol, lane);
-        __syncwarp();
-        if (band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, lane)) {          // :84-88
-          status = 1;
-          break;
-        }
-        // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
-        for (int k = lane; k < NY; k += 32) {
-          double hx = 0.0;
-          for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
-          const double dy = w[k] - dinv[k] * hx;
-          const double f3 = s[k] * y[k] - eps;
-          w[k] = dy;
-          dinv[k] = -(f3 + s[k] * dy) / (y[k] + tol);
-        }
-        __syncwarp();
-        const double a_s = ftb_linesearch(s, dinv, p.min_stepsize, lane);  // :93
-        const double a_y = ftb_linesearch(y, w, p.min_stepsize, lane);     // :94
-        if (a_s != a_s || a_y != a_y) {                                    // :96-100
-          status = 1;
-          break;
-        }
-        for (int c = lane; c < NRED; c += 32) x[PERM[c]] += a_s * sol[c];  // :103 (x uses α_s)
-        for (int k = lane; k < NY; k += 32) {
-          s[k] += a_s * dinv[k];                                           // :104
-          y[k] += a_y * w[k];                                              // :105
-        }
-        __syncwarp();
-        kkt = kkt_new;                                                     // :107
-        ++inner;                                                           // :108
-        ++steps;
-      }
-      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
-      ++outer;                                                             // :114
-    }
-    if (!parked && outer == p.max_outer) status = 1;                       // :117-119
-
-    for (int i = lane; i < NX; i += 32) p.x_out[inst * NX + i] = x[i];
-    for (int i = lane; i < NY; i += 32) {
-      p.y_out[inst * NY + i] = y[i];
-      p.s_out[inst * NY + i] = s[i];
-    }
-    if (lane == 0) {
-      p.kkt_out[inst] = kkt;
-      p.eps_out[inst] = eps;
-      p.outer_out[inst] = outer;
-      p.status_out[inst] = status;
-      p.steps_out[inst] = steps;
-      if (parked) {
-        p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
-      } else {
-        atomicAdd(p.counters + 1, (unsigned long long)steps);
-        if (status == 0) atomicAdd(p.counters + 2, 1ULL);
-      }
-    }
-    __syncwarp();
+    __syncwarp(smask);
   }
 }
 
@@ -554,14 +702,15 @@ extern "C" __global__ void __launch_bounds__(32 * SOLVE_WARPS, 1) mcp_solve_kern
 // through the same condensation with D = S Y⁻¹, NRHS_SENS right-hand sides per factorisation pass.
 // ------------------------------------------------------------------------------------------------
 #if HAS_JT
-extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel(const SensParams p) {
+extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel(const SensParams p) {
   extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int sl = threadIdx.x % SUB;
+  const int slot = threadIdx.x / SUB;
+  const unsigned smask = sub_mask(threadIdx.x & 31);
   load_shared_tables(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
-  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)warp * SENS_SMEM_DOUBLES;
+  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SENS_SMEM_DOUBLES;
   double* x = S + SENS_OFF_X;
   double* y = S + SENS_OFF_Y;
   double* s = S + SENS_OFF_S;
@@ -574,51 +723,51 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
 #if THETA_IN_SMEM
   double* th = S + SENS_OFF_TH;
 #endif
-  double* Cval = p.scratch + ((size_t)blockIdx.x * SENS_WARPS + warp) * SENS_SCRATCH;
+  double* Cval = p.scratch + ((size_t)blockIdx.x * SENS_INST + slot) * SENS_SCRATCH;
   double* UT = Cval + CVAL_DOUBLES;
   constexpr int NZ = NX + 2 * NY;
 
   for (;;) {
     unsigned long long inst = 0;
-    if (lane == 0) inst = atomicAdd(p.counters, 1ULL);
-    inst = __shfl_sync(FULLMASK, inst, 0);
+    if (sl == 0) inst = atomicAdd(p.counters, 1ULL);
+    inst = __shfl_sync(smask, inst, 0, SUB);
     if (inst >= (unsigned long long)p.B) break;
 #if THETA_IN_SMEM
-    for (int i = lane; i < NT; i += 32) th[i] = p.theta[inst * NT + i];
+    for (int i = sl; i < NT; i += SUB) th[i] = p.theta[inst * NT + i];
 #else
     const double* th = p.theta + inst * NT;
 #endif
-    for (int i = lane; i < NX; i += 32) x[i] = p.x[inst * NX + i];
-    for (int i = lane; i < NY; i += 32) {
+    for (int i = sl; i < NX; i += SUB) x[i] = p.x[inst * NX + i];
+    for (int i = sl; i < NY; i += SUB) {
       y[i] = p.y[inst * NY + i];
       s[i] = p.s[inst * NY + i];
     }
-    __syncwarp();
-    mcp_eval_sens_par(lane, x, y, th, jv, jtv);
-    __syncwarp();
-    for (int k = lane; k < NY; k += 32) dinv[k] = y[k] / s[k];  // D⁻¹ with D = s/y (tol = 0)
+    __syncwarp(smask);
+    mcp_eval_sens_par(sl, x, y, th, jv, jtv);
+    __syncwarp(smask);
+    for (int k = sl; k < NY; k += SUB) dinv[k] = y[k] / s[k];  // D⁻¹ with D = s/y (tol = 0)
     if (p.z_p)
-      for (int i = lane; i < NZ * p.P; i += 32) p.z_p[inst * NZ * p.P + i] = 0.0;
-    __syncwarp();
+      for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = 0.0;
+    __syncwarp(smask);
     int bad = 0;
     for (int q0 = 0; q0 < NT; q0 += NRHS_SENS) {
       const int nq = min(NRHS_SENS, NT - q0);
-      for (int i = lane; i < NRHS_SENS * NY; i += 32) wq[i] = 0.0;
-      for (int i = lane; i < NRHS_SENS * NRED; i += 32) sol[i] = 0.0;
-      assemble_matrix(Cval, W, jv, th, dinv, 0.0, lane);
-      __syncwarp();
+      for (int i = sl; i < NRHS_SENS * NY; i += SUB) wq[i] = 0.0;
+      for (int i = sl; i < NRHS_SENS * NRED; i += SUB) sol[i] = 0.0;
+      assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
+      __syncwarp(smask);
       // right-hand sides r = −∇F_θ[:, q]:  G rows go to the reduced rhs, H rows to w = D⁻¹ r₂
       for (int rq = 0; rq < nq; ++rq) {
         const int q = q0 + rq;
-        for (int e = Q_PTR[q] + lane; e < Q_PTR[q + 1]; e += 32) {
+        for (int e = Q_PTR[q] + sl; e < Q_PTR[q + 1]; e += SUB) {
           const double v = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
           const int row = Q_ROW[e];
           if (row < NX) sol[rq * NRED + IPERM[row]] = v;
           else wq[rq * NY + (row - NX)] = dinv[row - NX] * v;
         }
       }
-      __syncwarp();
-      for (int i = lane; i < NRED; i += 32) {
+      __syncwarp(smask);
+      for (int i = sl; i < NRED; i += SUB) {
         for (int rq = 0; rq < nq; ++rq) {
           double r = sol[rq * NRED + i];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
@@ -626,8 +775,8 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
           sol[rq * NRED + i] = r;
         }
       }
-      __syncwarp();
-      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, lane)) {
+      __syncwarp(smask);
+      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, sl, smask)) {
         bad = 1;
         break;
       }
@@ -636,7 +785,7 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
         const int q = q0 + rq;
         const double* so = sol + rq * NRED;
         double tb = 0.0;
-        for (int c = lane; c < NRED; c += 32) {
+        for (int c = sl; c < NRED; c += SUB) {
           const double zx = so[c];
           const int row = PERM[c];
           if (p.dzdtheta) p.dzdtheta[(inst * NT + q) * NZ + row] = zx;
@@ -645,7 +794,7 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
             for (int pp = 0; pp < p.P; ++pp)
               p.z_p[(inst * p.P + pp) * NZ + row] += zx * p.theta_p[(inst * p.P + pp) * NT + q];
         }
-        for (int k = lane; k < NY; k += 32) {
+        for (int k = sl; k < NY; k += SUB) {
           double hx = 0.0;
           for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * so[H_COL[e]];
           const double zy = wq[rq * NY + k] - dinv[k] * hx;
@@ -663,14 +812,14 @@ extern "C" __global__ void __launch_bounds__(32 * SENS_WARPS, 1) mcp_sens_kernel
             }
         }
         if (p.thetabar) {
-          tb = warp_sum(tb);
-          if (lane == 0) p.thetabar[inst * NT + q] = tb;
+          tb = sub_sum(tb, smask);
+          if (sl == 0) p.thetabar[inst * NT + q] = tb;
         }
       }
-      __syncwarp();
+      __syncwarp(smask);
     }
-    if (lane == 0 && p.status_out) p.status_out[inst] = bad;
-    __syncwarp();
+    if (sl == 0 && p.status_out) p.status_out[inst] = bad;
+    __syncwarp(smask);
   }
 }
 #endif  // HAS_JT

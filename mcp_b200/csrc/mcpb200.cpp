@@ -320,11 +320,11 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
   p.pass = 0;
-  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, 32u * P.ipc_solve, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, (unsigned)(P.sub * P.ipc_solve), 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
   st->launches = 1;
   if (budget > 0) {
     p.pass = 1;
-    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, 32u * P.ipc_solve, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, (unsigned)(P.sub * P.ipc_solve), 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
     st->launches = 2;
   }
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
@@ -344,7 +344,7 @@ int launch_sens(mcpb200_problem* h, DeviceState* st, SensParams& p, cudaStream_t
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
-  CU_TRY(h, driver().LaunchKernel(st->f_sens, grid, 1, 1, 32u * P.ipc_sens, 1, 1, (unsigned)P.smem_sens, (CUstream)stream, args, nullptr));
+  CU_TRY(h, driver().LaunchKernel(st->f_sens, grid, 1, 1, (unsigned)(P.sub * P.ipc_sens), 1, 1, (unsigned)P.smem_sens, (CUstream)stream, args, nullptr));
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
   st->timed = true;
   st->launches = 1;
@@ -457,7 +457,7 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->n_jac_constant = P.n_const_entries;
   info->n_assembly_dests = (int)P.d_row.size();
   info->n_assembly_terms = (int)P.t_coef.size();
-  info->threads_per_instance = 32;
+  info->threads_per_instance = P.sub;
   info->instances_per_cta = P.ipc_solve;
   info->ctas_per_sm = 1;
   info->smem_bytes_per_cta = (int)P.smem_solve;

@@ -334,13 +334,14 @@ struct Emitter {
   // shared between groups are recomputed per group.
   // outs[i] = {root node, "target[index]"}.
   void partitioned(std::ostringstream& os, const std::string& name, const std::string& params,
-                   const std::string& args, const std::vector<std::pair<int32_t, std::string>>& outs) const {
+                   const std::string& args, const std::vector<std::pair<int32_t, std::string>>& outs,
+                   int max_parts) const {
     std::vector<int32_t> roots;
     for (auto& o : outs) roots.push_back(o.first);
     const std::vector<int> cost = incremental_cost(roots);
     long total = 0;
     for (int c : cost) total += c;
-    const int K = (int)std::max<long>(1, std::min<long>(32, std::min<long>((long)outs.size(), total / 24 + 1)));
+    const int K = (int)std::max<long>(1, std::min<long>(max_parts, std::min<long>((long)outs.size(), total / 24 + 1)));
     std::vector<size_t> begin(K + 1, outs.size());
     begin[0] = 0;
     {
@@ -635,9 +636,33 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     lay << "#define " << name << " " << off << "\n";
     off = even(off + n);
   };
+  // The "window" region of shared memory is, over one Newton step: storage of G, term buffer of the
+  // two-phase assembly, the factorisation window (or, with register-resident rows, just two staging rows),
+  // and the cp.async ring of the back substitution.
+  // Lanes per instance: a half-warp when the window has at most 16 rows (two instances then share every
+  // instruction of the factorisation), else the whole warp.  MCPB200_SUB / MCPB200_REGWIN override (A/B tests).
+  P.sub = (P.R <= 8 && P.nrhs_sens <= 16) ? 16 : 32;   // measured: pairing pays for tiny windows (README QP 2x)
+  if (const char* e = getenv("MCPB200_SUB")) {
+    const int v = atoi(e);
+    if (v == 32 || (v == 16 && P.R <= 16 && P.nrhs_sens <= 16)) P.sub = v;
+  }
+  P.regwin = 0;
+  if (const char* e = getenv("MCPB200_REGWIN")) P.regwin = atoi(e) != 0;
+  const int64_t nterms_all = (int64_t)P.t_coef.size();
+  const int uts = (P.WC + 1) & ~1;   // UT row stride: even ⇒ 16-byte rows for cp.async.cg
+  auto window_doubles = [&](int ws, int nrhs) -> int64_t {
+    const bool regwin = P.regwin && P.R <= P.sub && P.WC + nrhs <= 40;
+    if (!regwin) return (int64_t)P.R * ws;
+    int64_t w = 2 * (int64_t)ws;
+    w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
+    if (nterms_all <= 1024) w = std::max(w, nterms_all);                    // two-phase assembly buffer
+    if (nx <= 1024) w = std::max<int64_t>(w, nx);                          // G alias
+    return w;
+  };
+  const int64_t win_solve = window_doubles(P.WS1, 1), win_sens = window_doubles(P.WSS, P.nrhs_sens);
   // G is consumed (residual norm, condensed rhs) before the window is used, so it shares the window's
   // storage whenever it fits; H[k] is consumed by the very lane/iteration that writes w[k], so H lives in w.
-  const bool g_alias = (int64_t)P.R * P.WS1 >= nx;
+  const bool g_alias = win_solve >= nx;
   place("SOLVE_OFF_X", nx);
   place("SOLVE_OFF_Y", ny);
   place("SOLVE_OFF_S", ny);
@@ -649,7 +674,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   place("SOLVE_OFF_SOL", N);
   if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
   if (g_alias) lay << "#define SOLVE_OFF_G " << off << "\n";
-  place("SOLVE_OFF_WIN", (int64_t)P.R * P.WS1);
+  place("SOLVE_OFF_WIN", win_solve);
   const int64_t solve_doubles = off;
   off = 0;
   place("SENS_OFF_X", nx);
@@ -661,13 +686,15 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   place("SENS_OFF_WQ", (int64_t)P.nrhs_sens * ny);
   place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
   if (P.theta_in_smem) place("SENS_OFF_TH", nt);
-  place("SENS_OFF_WIN", (int64_t)P.R * P.WSS);
+  place("SENS_OFF_WIN", win_sens);
   const int64_t sens_doubles = off;
   const int64_t nd = (int64_t)P.d_row.size();
   const int64_t shared_table_doubles = even(((int64_t)(N + 1) * 4 + nd * 2 + 7) / 8);
-  auto warps_for = [&](int64_t doubles) {
+  auto warps_for = [&](int64_t doubles) {  // instances per CTA
     int64_t w = (kSmemBudget - shared_table_doubles * 8) / (doubles * 8);
-    return (int)std::max<int64_t>(0, std::min<int64_t>(w, 16));
+    w = std::min<int64_t>(w, 768 / P.sub);   // ≤ 768 threads per CTA keeps ≥ 85 registers per thread
+    if (P.sub == 16) w &= ~int64_t(1);       // whole warps
+    return (int)std::max<int64_t>(0, w);
   };
   P.ipc_solve = warps_for(solve_doubles);
   P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
@@ -680,7 +707,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
   P.smem_sens = (shared_table_doubles + sens_doubles * P.ipc_sens) * 8;
   const int64_t cval_doubles = even(nd) + 2;
-  P.scratch_doubles_solve = cval_doubles + even((int64_t)N * P.WC) + 2;
+  P.scratch_doubles_solve = cval_doubles + even((int64_t)N * uts) + 2;
   P.scratch_doubles_sens = P.scratch_doubles_solve;
   // banded LU with partial pivoting + forward/back substitution, dense-in-band count
   {
@@ -696,14 +723,15 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   os << "#define WS1 " << P.WS1 << "\n#define WSS " << P.WSS << "\n#define NRHS_SENS " << P.nrhs_sens << "\n";
   os << "#define NJV " << njv << "\n#define NJTV " << njtv << "\n#define ND " << P.d_row.size() << "\n";
   os << "#define THETA_IN_SMEM " << P.theta_in_smem << "\n#define HAS_JT " << (P.has_jt ? 1 : 0) << "\n";
-  os << "#define SOLVE_WARPS " << P.ipc_solve << "\n#define SENS_WARPS " << P.ipc_sens << "\n";
+  os << "#define SUB " << P.sub << "\n#define SOLVE_INST " << P.ipc_solve << "\n#define SENS_INST " << P.ipc_sens << "\n";
   os << "#define SOLVE_SMEM_DOUBLES " << solve_doubles << "\n#define SENS_SMEM_DOUBLES " << sens_doubles << "\n";
   os << "#define SOLVE_SCRATCH " << P.scratch_doubles_solve << "\n#define SENS_SCRATCH " << P.scratch_doubles_sens << "\n";
   {
-    const int64_t win1 = (int64_t)P.R * P.WS1, wins = (int64_t)P.R * P.WSS, nterms = (int64_t)P.t_coef.size();
+    const int64_t win1 = win_solve, wins = win_sens, nterms = (int64_t)P.t_coef.size();
     // the window's storage doubles as the term buffer of the two-phase assembly and as the cp.async ring
     os << "#define NTERMS " << nterms << "\n#define ASM_TWO_PHASE " << ((nterms <= std::min(win1, wins)) ? 1 : 0) << "\n";
-    os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / P.WC)) << "\n";
+    os << "#define UTS " << uts << "\n#define REGWIN " << P.regwin << "\n";
+    os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
   os << lay.str();
@@ -761,7 +789,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     E.partitioned(os, "mcp_eval_newton",
                   "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                   "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
-                  "x, y, th, g, h, jv", outs);
+                  "x, y, th, g, h, jv", outs, P.sub);
   }
   if (P.has_jt) {
     os << "// computed entries of ∇F_z and ∇F_θ at the solution (src/AutoDiff.jl:27-37)\n";
@@ -774,7 +802,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       E.partitioned(os, "mcp_eval_sens",
                     "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                     "double* __restrict__ jv, double* __restrict__ jtv",
-                    "x, y, th, jv, jtv", outs);
+                    "x, y, th, jv, jtv", outs, P.sub);
     }
   }
   os << kernel_template;

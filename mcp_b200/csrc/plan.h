@@ -69,7 +69,8 @@ struct Plan {
   std::vector<double> q_coef;
 
   // ---- launch configuration -----------------------------------------------------------------------
-  int threads_per_instance = 32;
+  int sub = 32;                       // lanes per instance (16: two instances per warp)
+  int regwin = 0;                     // window rows in registers (shuffle broadcast) instead of shared memory
   int ipc_solve = 1, ipc_sens = 1;    // instances (warps) per CTA
   int theta_in_smem = 1;
   int64_t smem_solve = 0, smem_sens = 0;
