@@ -190,35 +190,55 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
   constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
   constexpr int WPL = (WS + SUB - 1) / SUB;
 
-  constexpr int NPOS = WC + NRHS;
-  if constexpr (REGWIN && WR <= SUB && NPOS <= 40) {
+  // 2-D register layout: NPART lanes per window row, PW (even) consecutive positions each
+  constexpr int NPART = (WR <= SUB) ? ((SUB / WR) >= 4 ? 4 : ((SUB / WR) >= 2 ? 2 : 1)) : 1;
+  constexpr int PW = (((WC + NPART - 1) / NPART) + 1) & ~1;
+  constexpr int WCP = PW * NPART;               // padded matrix width
+  constexpr int ES = (WCP + NRHS + 3) & ~1;     // stride of the publish / staging rows (even, one pair of slack)
+  if constexpr (REGWIN && WR <= SUB && PW <= 40) {
     // ============ register-resident window ==========================================================
-    // Every sl keeps ITS window row in registers, in a layout relative to the pivot column: a[d] is the
-    // entry in column j+d (d = 0 … WC-1), a[WC+q] the q-th right-hand side.  Eliminating column j and
-    // advancing the window are one operation, a[d] ← a[d+1] − m·u[d+1]: the FMA's destination register does
-    // the shift for free, position 0 is always the pivot column, and the loop body stays small (rolled).
-    // The pivot row is broadcast with shuffles; shared memory only stages the entering row.  (Measured on
-    // the shared-memory variant below: the smem pipe sat at 60 % of peak re-loading/re-storing window rows.)
-    double a[NPOS];
-    double* E = W;  // two staging rows of WS doubles, alternating between steps
+    // Window rows live in REGISTERS for their whole life in the window, each row split over NPART lanes:
+    // lane (row, part) holds a[i] = the entry in column j + part·PW + i — a layout relative to the pivot
+    // column, so eliminating column j and advancing the window are ONE operation,
+    //     a[i] ← a[i+1] − m·u[i+1],
+    // with the FMA's destination register doing the shift for free (position 0 is always the pivot column,
+    // the loop body stays small and rolled).  The pivot row is published once to shared memory and read back
+    // with aligned 128-bit broadcast loads; shared memory otherwise only stages the entering row.
+    // Why: with the window itself in shared memory (variant below) the smem pipe sat at 60 % of peak
+    // re-loading/re-storing rows, and broadcasting by shuffle costs the same crossbar as many wavefronts.
+    const bool active = sl < WR * NPART;
+    const int row = sl % WR;
+    const int part = active ? sl / WR : 0;
+    double a[PW], rh[NRHS];
+    double* Pb = W;       // published pivot row: WCP matrix positions, then the RHS
+    double* E = W + ES;   // two staging rows, alternating between steps
 #pragma unroll
-    for (int i = 0; i < NPOS; ++i) a[i] = 0.0;
-    for (int r = 0; r < WR; ++r) {  // rows 0 … WR-1, relative to column 0
-      for (int q = sl; q < WS; q += SUB) E[q] = 0.0;
-      __syncwarp(smask);
-      for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = __ldcg(Cval + e);  // columns < WC: no wrap yet
-      if (sl < NRHS) E[WC + sl] = sol[sl * NRED + r];
-      __syncwarp(smask);
-      if (sl == r) {
+    for (int i = 0; i < PW; ++i) a[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < NPOS; ++i) a[i] = E[i];
+    for (int q = 0; q < NRHS; ++q) rh[q] = 0.0;
+    for (int r = 0; r < WR; ++r) {  // rows 0 … WR-1, relative to column 0 (their columns are < WC: no wrap)
+      for (int q = sl; q < ES; q += SUB) E[q] = 0.0;
+      __syncwarp(smask);
+      for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = __ldcg(Cval + e);
+      if (sl < NRHS) E[WCP + sl] = sol[sl * NRED + r];
+      __syncwarp(smask);
+      if (active && row == r) {
+        const double2* src = reinterpret_cast<const double2*>(E + part * PW);
+#pragma unroll
+        for (int k = 0; k < PW / 2; ++k) {
+          const double2 v = src[k];
+          a[2 * k] = v.x;
+          a[2 * k + 1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) rh[q] = E[WCP + q];
       }
       __syncwarp(smask);
     }
-    int cj1 = (1 == WC) ? 0 : 1;  // (j+1) % WC: circular position of the column that becomes d = 0 next
+    int cj1 = (1 == WC) ? 0 : 1;  // (j+1) % WC: circular position of the column that becomes relative 0 next
 #pragma unroll 1
     for (int j = 0; j < NRED; ++j) {
-      double* Eb = E + (j & 1) * WS;
+      double* Eb = E + (j & 1) * ES;
       const int ienter = j + WR;
       int e0 = 0, e1 = 0;
       if (ienter < NRED) {
@@ -231,44 +251,57 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
         const int e = e0 + sl + SUB * k;
         pre[k] = (e < e1) ? __ldcg(Cval + e) : 0.0;
       }
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) {
-        const int q = sl + SUB * k;
-        if (q < WS) Eb[q] = 0.0;
-      }
+      for (int q = sl; q < ES; q += SUB) Eb[q] = 0.0;
       // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, row in the low byte ----
       unsigned key = 0;
-      if (sl < WR) key = ((unsigned)__double2hiint(fabs(a[0])) & 0xffffff00u) | (unsigned)(255 - sl);
+      if (active && part == 0) key = ((unsigned)__double2hiint(fabs(a[0])) & 0xffffff00u) | (unsigned)(255 - row);
       const unsigned best = __reduce_max_sync(smask, key);
       const int p = 255 - (int)(best & 0xffu);
       const double piv = __shfl_sync(smask, a[0], p, SUB);
       if (!(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) return 1;  // zero, NaN or Inf pivot
       const double rp = 1.0 / piv;
-      const double m = (sl < WR && sl != p) ? -(a[0] * rp) : 0.0;
-      // ---- retire the pivot row: its owner writes U row j out transposed, its RHS into sol -------------
-      if (sl == p) {
+      const double a0row = __shfl_sync(smask, a[0], row, SUB);       // my row's entry in the pivot column
+      double nx = __shfl_sync(smask, a[0], (sl + WR) % SUB, SUB);    // first entry of my row's next part
+      if (part == NPART - 1) nx = 0.0;
+      const double m = (active && row != p) ? -(a0row * rp) : 0.0;
+      // ---- publish the pivot row ----------------------------------------------------------------------------
+      if (active && row == p) {
+        double2* dst = reinterpret_cast<double2*>(Pb + part * PW);
+#pragma unroll
+        for (int k = 0; k < PW / 2; ++k) dst[k] = make_double2(a[2 * k], a[2 * k + 1]);
+        if (part == 0) {
+#pragma unroll
+          for (int q = 0; q < NRHS; ++q) Pb[WCP + q] = rh[q];
+        }
+      }
+      __syncwarp(smask);
+      // ---- retire it: U row j goes out transposed (coalesced over the lanes), its RHS into sol ------------
+      {
         const int tmax = min(WC - 1, NRED - 1 - j);
-        double* Uj = UT + (size_t)j * UTS;
-        __stcg(Uj, rp);
 #pragma unroll
-        for (int d = 1; d < WC; ++d)
-          if (d <= tmax) __stcg(Uj + d * (UTS + 1), a[d]);
-#pragma unroll
-        for (int q = 0; q < NRHS; ++q) sol[q * NRED + j] = a[WC + q];
+        for (int k = 0; k < CPW; ++k) {
+          const int t = sl + SUB * k;
+          if (t <= tmax) __stcg(UT + (size_t)(j + t) * UTS + t, (t == 0) ? rp : Pb[t]);
+        }
+        if (sl < NRHS) sol[sl * NRED + j] = Pb[WCP + sl];
       }
-      // ---- eliminate column j and slide the window: a[d] ← a[d+1] − m·u[d+1] --------------------------------
+      // ---- eliminate column j and slide the window: a[i] ← a[i+1] − m·u[i+1] ------------------------------
+      {
+        const double2* up = reinterpret_cast<const double2*>(Pb + part * PW);
+        double u[PW + 2];
 #pragma unroll
-      for (int d = 0; d + 1 < WC; ++d) {
-        const double u = __shfl_sync(smask, a[d + 1], p, SUB);
-        a[d] = fma(m, u, a[d + 1]);
-      }
-      a[WC - 1] = 0.0;  // column j+WC enters the window (structurally zero in every resident row)
+        for (int k = 0; k <= PW / 2; ++k) {  // PW/2 + 1 aligned pairs: my part and the first entry of the next
+          const double2 v = up[k];
+          u[2 * k] = v.x;
+          u[2 * k + 1] = v.y;
+        }
 #pragma unroll
-      for (int q = 0; q < NRHS; ++q) {
-        const double u = __shfl_sync(smask, a[WC + q], p, SUB);
-        a[WC + q] = fma(m, u, a[WC + q]);
+        for (int i = 0; i + 1 < PW; ++i) a[i] = fma(m, u[i + 1], a[i + 1]);
+        a[PW - 1] = (part == NPART - 1) ? 0.0 : fma(m, u[PW], nx);   // last part: column j+WCP enters, zero
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) rh[q] = fma(m, Pb[WCP + q], rh[q]);
       }
-      // ---- the entering row (relative to column j+1) takes over the retired sl ----------------------------
+      // ---- the entering row (relative to column j+1) takes over the retired row's lanes -----------------------
       __syncwarp(smask);
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
@@ -279,11 +312,18 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
           Eb[d] = pre[k];
         }
       }
-      if (sl < NRHS && ienter < NRED) Eb[WC + sl] = sol[sl * NRED + ienter];
+      if (sl < NRHS && ienter < NRED) Eb[WCP + sl] = sol[sl * NRED + ienter];
       __syncwarp(smask);
-      if (sl == p) {
+      if (active && row == p) {
+        const double2* src = reinterpret_cast<const double2*>(Eb + part * PW);
 #pragma unroll
-        for (int i = 0; i < NPOS; ++i) a[i] = Eb[i];
+        for (int k = 0; k < PW / 2; ++k) {
+          const double2 v = src[k];
+          a[2 * k] = v.x;
+          a[2 * k + 1] = v.y;
+        }
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) rh[q] = Eb[WCP + q];
       }
       cj1 = (cj1 + 1 == WC) ? 0 : cj1 + 1;
     }

@@ -646,14 +646,18 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     const int v = atoi(e);
     if (v == 32 || (v == 16 && P.R <= 16 && P.nrhs_sens <= 16)) P.sub = v;
   }
-  P.regwin = 0;
+  P.regwin = 1;
   if (const char* e = getenv("MCPB200_REGWIN")) P.regwin = atoi(e) != 0;
   const int64_t nterms_all = (int64_t)P.t_coef.size();
   const int uts = (P.WC + 1) & ~1;   // UT row stride: even ⇒ 16-byte rows for cp.async.cg
   auto window_doubles = [&](int ws, int nrhs) -> int64_t {
-    const bool regwin = P.regwin && P.R <= P.sub && P.WC + nrhs <= 40;
+    // mirrors the constexpr arithmetic of band_solve (kernel_template.cuh)
+    const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
+    const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
+    const int es = (pw * npart + nrhs + 3) & ~1;
+    const bool regwin = P.regwin && P.R <= P.sub && pw <= 40;
     if (!regwin) return (int64_t)P.R * ws;
-    int64_t w = 2 * (int64_t)ws;
+    int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
     w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
     if (nterms_all <= 1024) w = std::max(w, nterms_all);                    // two-phase assembly buffer
     if (nx <= 1024) w = std::max<int64_t>(w, nx);                          // G alias
