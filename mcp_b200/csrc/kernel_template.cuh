@@ -123,6 +123,7 @@ __device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, doubl
   // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
 #if ASM_TWO_PHASE
   // phase A, term-parallel (all table loads independent and coalesced): tmp[t] = coef·val(a)·[D⁻¹_k·val(b)]
+#pragma unroll 4
   for (int t = sl; t < NTERMS; t += SUB) {
     const int4 ti = T_I[t];  // {a, b, k, -}
     double v = T_COEF[t] * opval(ti.x, jv, th);
@@ -185,7 +186,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int NRHS, int WS>
 __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cval, double* __restrict__ UT,
                           double* __restrict__ sol, const int* __restrict__ rowptr,
-                          const unsigned short* __restrict__ cpos, int sl, unsigned smask) {
+                          const unsigned short* __restrict__ cpos, const double* __restrict__ jv,
+                          const double* __restrict__ th, const double* __restrict__ dinv, double* __restrict__ stage,
+                          int sl, unsigned smask) {
   constexpr int CPW = (WC + SUB - 1) / SUB;  // matrix positions per sl
   constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
   constexpr int WPL = (WS + SUB - 1) / SUB;
@@ -338,6 +341,45 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
     if (sl < NRHS) W[r * WS + WC + sl] = sol[sl * NRED + r];
   }
   __syncwarp(smask);
+#if DENSE_SCHUR
+  // Dense problems (the whole condensed matrix is resident: WR == NRED, WC == NRED): the Schur complement
+  // −G_y D⁻¹ H_x is accumulated as one rank-1 update per constraint k, (G_y[:,k] D⁻¹_k) ⊗ H_x[k,:], from two
+  // staged dense vectors — a term-by-term table would cost nx²·ny lookups (10⁶ per Newton step for the
+  // 100×100 QP).  Rows whose G_y entry is numerically zero are skipped.
+  {
+    double* hb = stage;            // H_x[k, :]   (new column ordering; WC == NRED so position == column)
+    double* gb = stage + STAGE_N;  // G_y[:, k]·D⁻¹_k (new row ordering)
+    constexpr int NPR = (NRED + 1) / 2;
+    for (int k = 0; k < NY; ++k) {
+      for (int i = sl; i < 2 * STAGE_N; i += SUB) stage[i] = 0.0;
+      __syncwarp(smask);
+#pragma unroll 4
+      for (int e = H_PTR[k] + sl; e < H_PTR[k + 1]; e += SUB) hb[H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+      const double dk = dinv[k];
+#pragma unroll 4
+      for (int e = GK_PTR[k] + sl; e < GK_PTR[k + 1]; e += SUB) gb[GK_ROW[e]] = GK_COEF[e] * opval(GK_CODE[e], jv, th) * dk;
+      __syncwarp(smask);
+      const double2* hb2 = reinterpret_cast<const double2*>(hb);
+#pragma unroll 1
+      for (int kk = 0; kk < RPL; ++kk) {
+        const int r = sl + SUB * kk;
+        const double gr = (r < NRED) ? gb[r] : 0.0;
+        if (gr != 0.0) {
+          double2* Wr2 = reinterpret_cast<double2*>(W + r * WS);
+#pragma unroll 4
+          for (int c2 = 0; c2 < NPR; ++c2) {
+            const double2 hv = hb2[c2];
+            double2 v = Wr2[c2];
+            v.x = fma(-gr, hv.x, v.x);
+            v.y = fma(-gr, hv.y, v.y);
+            Wr2[c2] = v;
+          }
+        }
+      }
+      __syncwarp(smask);
+    }
+  }
+#endif
 
   constexpr int NP = (WC + NRHS + 1) / 2;  // position pairs swept per row (matrix + rhs columns)
   constexpr int PB = (NP < 9) ? NP : 9;    // pairs per register batch
@@ -697,18 +739,20 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
     // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
     for (int i = sl; i < NRED; i += SUB) {
       double r = -g[R_GROW[i]];
+#pragma unroll 4
       for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
       sol[i] = r;
     }
     __syncwarp(smask);  // G (aliased onto the window) is dead from here on: the window becomes scratch
     assemble_matrix(Cval, W, jv, th, dinv, tol, sl, smask);
     __syncwarp(smask);
-    bool failed = band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, sl, smask) != 0;  // :84-88
+    bool failed = band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SOLVE_OFF_STAGE, sl, smask) != 0;  // :84-88
     double a_s = 1.0, a_y = 1.0;
     if (!failed) {
       // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
       for (int k = sl; k < NY; k += SUB) {
         double hx = 0.0;
+#pragma unroll 4
         for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
         const double dy = w[k] - dinv[k] * hx;
         const double f3 = s[k] * y[k] - eps;
@@ -816,7 +860,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
         }
       }
       __syncwarp(smask);
-      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, sl, smask)) {
+      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask)) {
         bad = 1;
         break;
       }

@@ -557,6 +557,21 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     return fail(MCPB200_ERR_UNSUPPORTED, buf);
   }
   if (N >= 65536 || P.WC >= 65536) return fail(MCPB200_ERR_UNSUPPORTED, "reduced dimension ≥ 65536");
+  // Dense problems: when the whole condensed matrix is resident (no banding to exploit) and the Schur
+  // product has far more terms than the matrix has entries, it is accumulated in-kernel as rank-1 updates
+  // (kernel_template.cuh, DENSE_SCHUR) instead of term by term.
+  {
+    size_t n_schur = 0;
+    for (auto& kv : dest)
+      for (auto& t : kv.second) n_schur += (t.k >= 0);
+    P.dense_schur = (P.R == N && P.WC == N && n_schur > 4 * dest.size()) ? 1 : 0;
+    if (const char* e = getenv("MCPB200_DENSE_SCHUR")) P.dense_schur = (atoi(e) != 0) && P.R == N && P.WC == N;
+    if (P.dense_schur)
+      for (auto& kv : dest) {
+        auto& v = kv.second;
+        v.erase(std::remove_if(v.begin(), v.end(), [](const Term& t) { return t.k >= 0; }), v.end());
+      }
+  }
   P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
   P.WS1 = stride_for(P.WC + 1);
   P.WSS = stride_for(P.WC + P.nrhs_sens);
@@ -612,6 +627,16 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       }
       P.h_ptr.push_back((int)P.h_coef.size());
     }
+    // G_y by column k, rows in the new ordering (dense Schur accumulation)
+    P.gk_ptr.push_back(0);
+    for (int k = 0; k < ny; ++k) {
+      for (auto& e : gy_by_k[k]) {
+        P.gk_row.push_back(P.iperm[e.row]);
+        P.gk_coef.push_back(P.jz_opnd[e.idx].coef);
+        P.gk_code.push_back(P.jz_opnd[e.idx].code);
+      }
+      P.gk_ptr.push_back((int)P.gk_row.size());
+    }
     // θ-Jacobian by column
     std::vector<std::vector<int>> by_q(std::max(nt, 1));
     for (size_t k = 0; k < P.jt_nodes.size(); ++k) by_q[P.jt_cols[k]].push_back((int)k);
@@ -648,6 +673,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
   P.regwin = 1;
   if (const char* e = getenv("MCPB200_REGWIN")) P.regwin = atoi(e) != 0;
+  if (P.dense_schur) P.regwin = 0;   // the rank-1 Schur accumulation works on the shared-memory window
   const int64_t nterms_all = (int64_t)P.t_coef.size();
   const int uts = (P.WC + 1) & ~1;   // UT row stride: even ⇒ 16-byte rows for cp.async.cg
   auto window_doubles = [&](int ws, int nrhs) -> int64_t {
@@ -677,6 +703,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   place("SOLVE_OFF_W", ny);
   place("SOLVE_OFF_SOL", N);
   if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
+  const int64_t stage_n = even(N);
+  place("SOLVE_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
   if (g_alias) lay << "#define SOLVE_OFF_G " << off << "\n";
   place("SOLVE_OFF_WIN", win_solve);
   const int64_t solve_doubles = off;
@@ -690,6 +718,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   place("SENS_OFF_WQ", (int64_t)P.nrhs_sens * ny);
   place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
   if (P.theta_in_smem) place("SENS_OFF_TH", nt);
+  place("SENS_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
   place("SENS_OFF_WIN", win_sens);
   const int64_t sens_doubles = off;
   const int64_t nd = (int64_t)P.d_row.size();
@@ -737,6 +766,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define UTS " << uts << "\n#define REGWIN " << P.regwin << "\n";
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
+  os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
   os << lay.str();
   {
@@ -770,6 +800,12 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   emit_table(os, "int", "H_CODE", P.h_code);
   emit_table(os, "int", "H_COL", P.h_col);
   emit_table(os, "double", "H_COEF", P.h_coef, true);
+  if (P.dense_schur) {
+    emit_table(os, "int", "GK_PTR", P.gk_ptr);
+    emit_table(os, "int", "GK_ROW", P.gk_row);
+    emit_table(os, "int", "GK_CODE", P.gk_code);
+    emit_table(os, "double", "GK_COEF", P.gk_coef, true);
+  }
   emit_table(os, "int", "PERM", P.perm);
   emit_table(os, "int", "IPERM", P.iperm);
   if (P.has_jt) {

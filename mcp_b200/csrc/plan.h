@@ -64,6 +64,10 @@ struct Plan {
   // (H_x v)_k = Σ_e coef·val(code)·v[col]  with col in the new ordering
   std::vector<int32_t> h_ptr, h_code, h_col;
   std::vector<double> h_coef;
+  // G_y by column k (rows in the new ordering): dense Schur accumulation
+  int dense_schur = 0;
+  std::vector<int32_t> gk_ptr, gk_row, gk_code;
+  std::vector<double> gk_coef;
   // θ-Jacobian, by column q: entries (row in [G;H], operand)
   std::vector<int32_t> q_ptr, q_row, q_code;
   std::vector<double> q_coef;

@@ -33,9 +33,11 @@ if len(sys.argv) > 3:
     src = open(sys.argv[3]).read().split("\n")
     marks = []
     for i, l in enumerate(src, 1):
-        for key in ("void mcp_eval_newton", "void mcp_eval_sens", "void assemble_matrix", "int band_solve", "// ---- back substitution",
-                    "double ftb_linesearch", "void __launch_bounds__(32 * SOLVE_WARPS", "void __launch_bounds__(32 * SENS_WARPS",
-                    "// ---- pivot search", "// ---- eliminate column", "// ---- the entering row", "// ---- retire", "// ---- my columns"):
+        for key in ("void mcp_eval_newton_p0(", "void mcp_eval_sens_p0(", "double opval(", "void assemble_matrix(", "int band_solve(",
+                    "// ============ register-resident window", "// ============ shared-memory window", "// ---- back substitution",
+                    "double ftb_linesearch(", "mcp_solve_kernel(const SolveParams", "mcp_sens_kernel(const SensParams",
+                    "// ---- pivot search", "// ---- publish the pivot row", "// ---- retire", "// ---- eliminate column",
+                    "// ---- the entering row", "// ---- control: advance my instance", "// ---- one Newton step"):
             if key in l: marks.append((i, key))
     marks.sort()
     reg = collections.Counter(); regi = collections.Counter()
