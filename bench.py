@@ -288,10 +288,12 @@ def main():
         flops_per_launch = info["flops_per_newton_step_band"] * tm["newton_steps"]
         achieved_tf = flops_per_launch / (tm["kernel_ms"] * 1e-3) / 1e12
         io_bytes = B * (8 * (nt + nx + 2 * ny) + 24)
-        traffic = None
+        traffic = None   # DRAM bytes of the solve launch: per-Newton-step figure from the committed ncu capture
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload)
+                per_step = json.load(f).get(args.workload, {}).get("dram_bytes_per_newton_step")
+            if per_step:
+                traffic = float(per_step) * tm["newton_steps"]
         except (OSError, ValueError):
             pass
         line = {
