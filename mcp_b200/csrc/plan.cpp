@@ -573,6 +573,16 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       }
   }
   P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
+  if (P.has_jt) {
+    // right-hand sides per factorisation pass: as many (≤ 16) as keep one instance within shared memory
+    auto sens_bytes = [&](int r) {
+      const int64_t fixed = (int64_t)nx + 3 * (int64_t)ny + (int64_t)P.jv_nodes.size() + (int64_t)P.jtv_nodes.size() +
+                            (nt <= kThetaSmemMax ? nt : 0) + 64;
+      const int64_t win = std::max<int64_t>((int64_t)P.R * (P.WC + r + 4), 1024);
+      return 8 * (fixed + (int64_t)r * (ny + N) + win);
+    };
+    while (P.nrhs_sens > 1 && sens_bytes(P.nrhs_sens) > kSmemBudget - 8192) P.nrhs_sens /= 2;
+  }
   P.WS1 = stride_for(P.WC + 1);
   P.WSS = stride_for(P.WC + P.nrhs_sens);
 
@@ -731,11 +741,16 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   };
   P.ipc_solve = warps_for(solve_doubles);
   P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
-  if (P.ipc_solve < 1 || P.ipc_sens < 1) {
+  if (P.ipc_solve < 1) {
     char buf[200];
     snprintf(buf, sizeof buf, "per-instance working set (%lld bytes) exceeds the %d-byte shared memory of one SM",
-             (long long)(std::max(solve_doubles, sens_doubles) * 8), kSmemBudget);
+             (long long)(solve_doubles * 8), kSmemBudget);
     return fail(MCPB200_ERR_UNSUPPORTED, buf);
+  }
+  if (P.has_jt && P.ipc_sens < 1) {
+    // the solve fits, the sensitivity solve does not: build without it (callers get MCPB200_ERR_NO_SENSITIVITIES)
+    P.has_jt = false;
+    P.ipc_sens = 1;
   }
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
   P.smem_sens = (shared_table_doubles + sens_doubles * P.ipc_sens) * 8;

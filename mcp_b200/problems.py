@@ -265,3 +265,116 @@ def lane_change_zero_input_x0(θ: np.ndarray, horizon: int = 10, n_eq: int = 80)
             out[base + 4 * t: base + 4 * t + 4] = st
             st = DI_A @ st
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cfg4: N-player masked trajectory game (player selection), horizon 30
+#       `examples/train_and_test_utils.jl:362-401` (`setup_trajectory_game(; environment, N)`),
+#       environment = square of side 10 (`setup_road_environment(; length)`, `:341-349`),
+#       built with `params_per_player = N + 2` (`examples/time_test.jl:23-24`): θ_i = [state(4); goal(2); mask(N)]
+# ------------------------------------------------------------------------------------------------
+def masked_game(N: int = 4, horizon: int = 30, length: float = 10.0,
+                compute_sensitivities: bool = True) -> ParametricGame:
+    """nx = 10·N·H, ny = H·(12N+1), nθ = N·(N+6)  (SURVEY.md §8 table)."""
+    H = horizon
+    h = 0.5 * length
+    halfspaces = [((0.0, -1.0), h), ((1.0, 0.0), h), ((0.0, 1.0), h), ((-1.0, 0.0), h)]
+    state_lb, state_ub = np.array([-np.inf, -np.inf, -2.0, -2.0]), np.array([np.inf, np.inf, 2.0, 2.0])   # :394
+    ctrl_lb, ctrl_ub = np.array([-1.0, -1.0]), np.array([1.0, 1.0])                                        # :395
+
+    def objective(ii):
+        def f(x, θi):                                        # stage cost `:364-370`, mean over time `:372-374`
+            xs, us = _unpack_trajectory(x, H, N)
+            goal, mask = θi[4:6], θi[6:6 + N]                # θi[end-(N+1):end-N], θi[end-(N-1):end]
+            total = 0.0
+            for t in range(H):
+                xi, ui = xs[t][4 * ii: 4 * ii + 4], us[t][2 * ii: 2 * ii + 2]
+                c = ((xi[0] - goal[0]) ** 2 + (xi[1] - goal[1]) ** 2 + xi[2] ** 2 + xi[3] ** 2
+                     + 0.1 * (ui[0] ** 2 + ui[1] ** 2))
+                for jj in range(N):
+                    if jj != ii:
+                        xj = xs[t][4 * jj: 4 * jj + 4]
+                        c = c + 2.0 * (mask[ii] * mask[jj]) / ((xi[0] - xj[0]) ** 2 + (xi[1] - xj[1]) ** 2)
+                total = total + c
+            return total / H
+        return f
+
+    def shared_equality(x, θ):                               # `examples/utils.jl:109-123`
+        xs, us = _unpack_trajectory(x, H, N)
+        init = np.concatenate([θ[i][:4] for i in range(N)])
+        rows = list(xs[0] - init)
+        for t in range(1, H):
+            nxt = np.concatenate([DI_A @ xs[t - 1][4 * i: 4 * i + 4] + DI_B @ us[t - 1][2 * i: 2 * i + 2]
+                                  for i in range(N)])
+            rows += list(xs[t] - nxt)
+        return np.array(rows, dtype=object)
+
+    def shared_inequality(x, θ):                             # `examples/utils.jl:126-155`
+        xs, us = _unpack_trajectory(x, H, N)
+        h1 = [1.0 + 0.0 * xs[t][0] for t in range(H)]        # coupling_constraints returns [1] per stage (`:380-388`)
+        h2 = []
+        for xj in xs:
+            for i in range(N):
+                p = xj[4 * i: 4 * i + 2]
+                for (a, b) in halfspaces:
+                    h2.append(-(a[0] * p[0] + a[1] * p[1]) + b)
+        h3, h4 = [], []
+        clb, cub = np.tile(ctrl_lb, N), np.tile(ctrl_ub, N)
+        slb, sub = np.tile(state_lb, N), np.tile(state_ub, N)
+        for uj in us:
+            h3 += box_constraints(uj, clb, cub)
+        for xj in xs:
+            h4 += box_constraints(xj, slb, sub)
+        return np.array(h1 + h2 + h3 + h4, dtype=object)
+
+    return ParametricGame(
+        test_point=[np.zeros(6 * H)] * N, test_parameter=[np.zeros(4 + 2 + N)] * N,
+        problems=[OptimizationProblem(objective=objective(i)) for i in range(N)],
+        shared_equality=shared_equality, shared_inequality=shared_inequality,
+        compute_sensitivities=compute_sensitivities)
+
+
+def masked_game_thetas(B: int, N: int = 4, seed: int = 1, side: float = 5.0, min_dist: float = 1.0,
+                       all_masks: bool = True) -> np.ndarray:
+    """Scenario distribution of `scripts/data_generation.py:5-38,52-55`: positions and goals ~ U[-side/2, side/2]²
+    with pairwise distance ≥ min_dist, zero velocity; θ_i = [state(4); goal(2); mask(N)], player 1 carries the
+    mask (ego = 1, the others swept over {0,1}), the other players all ones
+    (`examples/parametric_masked_game_solver.jl:19`, `game_with_masks.jl:13,24`)."""
+    rng = np.random.default_rng(seed)
+
+    def spread():
+        pts = []
+        while len(pts) < N:
+            p = rng.uniform(-0.5 * side, 0.5 * side, 2)
+            if all(np.hypot(*(p - q)) >= min_dist for q in pts):
+                pts.append(p)
+        return np.array(pts)
+
+    nθ = N * (N + 6)
+    θ = np.zeros((nθ, B), order="F")
+    n_masks = 2 ** (N - 1)
+    scenario = None
+    for b in range(B):
+        if scenario is None or not all_masks or b % n_masks == 0:
+            scenario = (spread(), spread())
+        pos, goal = scenario
+        m = b % n_masks if all_masks else n_masks - 1
+        ego_mask = np.array([1.0] + [float((m >> k) & 1) for k in range(N - 1)])
+        for i in range(N):
+            base = i * (N + 6)
+            θ[base: base + 2, b] = pos[i]
+            θ[base + 4: base + 6, b] = goal[i]
+            θ[base + 6: base + 6 + N, b] = ego_mask if i == 0 else 1.0
+    return θ
+
+
+def masked_game_x0(θ: np.ndarray, N: int = 4, horizon: int = 30) -> np.ndarray:
+    """Stay-at-rest rollout initial guess (zero-input trajectory from zero velocity, `examples/utils.jl:181-192`)."""
+    B = θ.shape[1]
+    H = horizon
+    out = np.zeros((10 * N * H, B), order="F")
+    for i in range(N):
+        st = θ[i * (N + 6): i * (N + 6) + 4]
+        for t in range(H):
+            out[i * 6 * H + 4 * t: i * 6 * H + 4 * t + 4] = st
+    return out

@@ -323,3 +323,28 @@ def test_large_batch_properties(lane_game):
         elif ref.status[k] == 1 and sol.status[b] == 1:
             agree += 1
     assert agree >= 62
+
+
+# ---- cfg4: masked N-player game (examples/train_and_test_utils.jl:362-401), N = 4, horizon 30 ------------------
+def test_masked_game_n4():
+    """nx = 1200, ny = 1470, nθ = 40: all 2^(N-1) ego masks of two scenarios, stay-at-rest initial guess, tol 1e-4
+    (the application's settings), against the C oracle; plus the sensitivity backward error."""
+    from oracle import c_oracle as CO
+    game = problems.masked_game(4, 30)
+    mcp = game.mcp
+    assert (mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension) == (1200, 1470, 40)
+    Θ = problems.masked_game_thetas(16, 4, seed=1)
+    x0 = problems.masked_game_x0(Θ, 4, 30)
+    sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
+    ref = CO.solve_batch(mcp.ir, Θ, x0=x0, tol=1e-4)
+    np.testing.assert_array_equal(sol.status, ref.status)
+    assert (sol.status == 0).sum() >= 12
+    for b in np.nonzero(ref.status == 0)[0]:
+        assert abs(int(sol.newton_steps[b]) - int(ref.newton_steps[b])) <= 1
+        assert rel_err(sol.x[:, b], ref.x[:, b]) <= RTOL and rel_err(sol.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
+    # masking a player out changes the ego's plan: the sweep must not return identical trajectories
+    assert np.max(np.abs(sol.x[:, 0] - sol.x[:, 7])) > 1e-3
+    from mcp_b200 import solve_pullback
+    g = solve_pullback(mcp, sol, Θ, 2 * sol.x, None, None)
+    assert g.shape == (40, 16) and np.all(np.isfinite(g[:, sol.status == 0]))

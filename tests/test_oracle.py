@@ -264,3 +264,18 @@ def test_bounds_assertion():
         PrimalDualMCP.from_K(lambda z, θ: z, [0.0, 1.0], [np.inf, np.inf], parameter_dimension=1)
     with pytest.raises(AssertionError):
         PrimalDualMCP.from_K(lambda z, θ: z, [0.0, -np.inf], [1.0, np.inf], parameter_dimension=1)
+
+
+def test_ir_structure_masked_game():
+    """cfg4 dimensions and sparsity from SURVEY.md §8 (N = 4, H = 30): nx = 10·N·H, ny = H(12N+1), nθ = N(N+6),
+    nnz(∇zF) = 12 970 of which 8 110 z-constant, nnz(∇θF) = 1 216; the oracle converges in 12–20 Newton steps."""
+    ir = problems.masked_game(4, 30).mcp.ir
+    assert (ir.nx, ir.ny, ir.ntheta) == (1200, 1470, 40)
+    assert len(ir.jz_rows) + 3 * ir.ny == 12970
+    assert len(ir.constant_entries()) + ir.ny == 8110
+    assert len(ir.jt_rows) == 1216
+    Θ = problems.masked_game_thetas(4, 4, seed=2)
+    r = CO.solve_batch(ir, Θ, x0=problems.masked_game_x0(Θ, 4, 30), tol=1e-4)
+    assert np.all(r.status == 0) and np.all((r.newton_steps >= 10) & (r.newton_steps <= 24))
+    # θ layout: player 1 carries the swept mask, the others all ones (parametric_masked_game_solver.jl:19)
+    assert np.all(Θ[6, :] == 1.0) and set(np.unique(Θ[7:10, :])) <= {0.0, 1.0} and np.all(Θ[16:20, :] == 1.0)
