@@ -348,3 +348,31 @@ def test_masked_game_n4():
     from mcp_b200 import solve_pullback
     g = solve_pullback(mcp, sol, Θ, 2 * sol.x, None, None)
     assert g.shape == (40, 16) and np.all(np.isfinite(g[:, sol.status == 0]))
+
+
+def test_lane_change_parity_statistics(lane_game):
+    """1 024 random lane-change instances against the C oracle: how often does the GPU follow the oracle's
+    trajectory to the bar (same status, Newton steps within ±1, x/y/s within 1e-6 relative)?  Decisions taken
+    at exact floating-point boundaries (kkt_error vs ϵ, the linesearch predicate) may legitimately flip, so the
+    requirement is ≥ 99 %, and every solved instance must at least reach the same status."""
+    from oracle import c_oracle as CO
+    mcp = lane_game.mcp
+    B = 1024
+    Θ = problems.lane_change_thetas(B, seed=2024)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    ref = CO.solve_batch(mcp.ir, Θ, tol=1e-6)
+    same_status = sol.status == ref.status
+    solved = ref.status == 0
+    ok = same_status.copy()
+    worst = 0.0
+    for b in np.nonzero(solved & same_status)[0]:
+        e = max(rel_err(sol.x[:, b], ref.x[:, b]), rel_err(sol.y[:, b], ref.y[:, b]), rel_err(sol.s[:, b], ref.s[:, b]))
+        steps_ok = abs(int(sol.newton_steps[b]) - int(ref.newton_steps[b])) <= 1
+        ok[b] = steps_ok and e <= RTOL
+        if steps_ok:
+            worst = max(worst, e)
+    print(f"parity: {ok.sum()}/{B} to the bar, status agreement {same_status.sum()}/{B}, "
+          f"identical step counts {int((sol.newton_steps[solved] == ref.newton_steps[solved]).sum())}/{int(solved.sum())}, "
+          f"worst rel err among step-matched {worst:.2e}")
+    assert same_status.mean() >= 0.995
+    assert ok.mean() >= 0.99
