@@ -575,6 +575,627 @@ __device__ __forceinline__ double ftb_linesearch(const double* __restrict__ v, c
   return __longlong_as_double(0x7ff8000000000000LL);  // NaN (:131)
 }
 
+#if DENSE_KERNEL
+// ------------------------------------------------------------------------------------------------
+// Dense solve kernel (plans whose whole condensed matrix is resident and whose Schur product is dense,
+// e.g. the QP configs): ONE CTA of 256 threads per instance, two CTAs per SM.
+//   * G/H evaluation split over up to 256 generated parts (thread i evaluates part i);
+//   * C = G_x + tol·I − G_y D⁻¹ H_x : the direct part is written dest-parallel, the Schur part is a
+//     register-tiled rank-k update — thread (ti, tj) of a 16×16 grid owns a TR×TR tile of C in registers
+//     and consumes constraints in blocks of DKB, staged (scaled by D⁻¹) into shared memory;
+//   * LU with partial pivoting on the shared-memory matrix, threads mapped (row, column half), RHS as an
+//     extra column; pivot rows stay in place (no scratch), a pivot order array drives the column-sweep back
+//     substitution.
+// The solver logic is the same literal restatement of src/solver.jl:63-121 as in mcp_solve_kernel.
+// ------------------------------------------------------------------------------------------------
+#define DT 256
+#define DKB 8
+#define DTR ((NRED + 15) / 16)  // register tile edge
+#define DNP (16 * DTR)          // padded dimension of the staged vectors
+
+__device__ __forceinline__ double blk_nanmax(double v, double* red, int t) {
+  v = sub_nanmax(v, FULLMASK);
+  __syncthreads();
+  if ((t & 31) == 0) red[t >> 5] = v;
+  __syncthreads();
+  double r = red[0];
+#pragma unroll
+  for (int i = 1; i < DT / 32; ++i) r = nanmax(r, red[i]);
+  return r;
+}
+
+// `fraction_to_the_boundary_linesearch` (src/solver.jl:127-138) with the whole CTA
+__device__ __forceinline__ double blk_ftb_linesearch(const double* __restrict__ v, const double* __restrict__ d,
+                                                     double min_step, int t) {
+  const double c = 1.0 - 0.995;
+  double alpha = 1.0;
+  for (int it = 0; it < 1200; ++it) {
+    bool viol = false;
+    for (int k = t; k < NY; k += DT) viol = viol || (v[k] + alpha * d[k] < c * v[k]);  // :129
+    if (!__syncthreads_or(viol)) return alpha;
+    if (alpha < min_step) break;  // :130
+    alpha *= 0.5;                 // :134
+  }
+  return __longlong_as_double(0x7ff8000000000000LL);
+}
+
+#if DENSE_KERNEL == 2
+extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const SolveParams p) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  double* x = smem + DENSE_OFF_X;
+  double* y = smem + DENSE_OFF_Y;
+  double* s = smem + DENSE_OFF_S;
+  double* g = smem + DENSE_OFF_G;
+  double* w = smem + DENSE_OFF_W;        // H rows, then w, then δy
+  double* dinv = smem + DENSE_OFF_DINV;  // D⁻¹, then δs
+  double* sol = smem + DENSE_OFF_SOL;
+  double* jv = smem + DENSE_OFF_JV;      // computed Jacobian entries (none for the QP configs)
+  double* W = smem + DENSE_OFF_WIN;      // NRED rows × WS1 (column NRED = right-hand side)
+  double* gbs = smem + DENSE_OFF_STG;    // DKB × DNP : G_y[:, k]·D⁻¹_k
+  double* hbs = gbs + DKB * DNP;         // DKB × DNP : H_x[k, :]
+  double* part = smem + DENSE_OFF_PART;  // 2 × 128 partial sums
+  double* red = smem + DENSE_OFF_RED;    // 16 doubles of reduction scratch
+  double* rd = smem + DENSE_OFF_RD;      // reciprocal pivots
+  double* Hc = smem + DENSE_OFF_HC;      // H_x cached for the whole solve: NY rows × DENSE_HCS (new column ordering)
+  double* xt = smem + DENSE_OFF_XT;      // x in the new ordering
+  double* gh0 = smem + DENSE_OFF_G0;     // G(0;θ), H(0;θ)
+  constexpr int HCS = DENSE_HCS;
+  int* ord = reinterpret_cast<int*>(smem + DENSE_OFF_ORD);  // pivot row of each elimination step
+  __shared__ unsigned long long sh_q;
+  __shared__ unsigned sh_key[DT / 32];
+#if THETA_IN_SMEM
+  double* th = smem + DENSE_OFF_TH;
+#else
+  const double* th = p.theta;
+#endif
+  const double tol = p.tol;
+  constexpr int WS = WS1;
+  const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+  const int r_ = t & 127, hf = t >> 7;   // (row, column half) mapping of the factorisation
+  const int ti = t >> 4, tj = t & 15;    // 16×16 tile grid of the Schur update
+
+  for (;;) {
+    __syncthreads();
+    if (t == 0) sh_q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+    __syncthreads();
+    unsigned long long inst = sh_q;
+    if (p.pass) {
+      if (inst >= n_deferred) break;
+      inst = (unsigned long long)p.deferred[inst];
+    } else if (inst >= (unsigned long long)p.B) {
+      break;
+    }
+#if THETA_IN_SMEM
+    for (int i = t; i < NT; i += DT) th[i] = p.theta[inst * NT + i];
+#else
+    th = p.theta + inst * NT;
+#endif
+    double eps = 1.0;                                        // :67
+    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // :68
+    int status = 0, outer = 1, steps = 0;                    // :69-70
+    if (p.pass) {
+      for (int i = t; i < NX; i += DT) x[i] = p.x_out[inst * NX + i];
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y_out[inst * NY + i];
+        s[i] = p.s_out[inst * NY + i];
+      }
+      eps = p.eps_out[inst];
+      kkt = p.kkt_out[inst];
+      outer = p.outer_out[inst];
+      steps = p.steps_out[inst];
+    } else {
+      for (int i = t; i < NX; i += DT) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      }
+    }
+    __syncthreads();
+    // ---- once per solve: cache H_x (θ-only) in shared memory and evaluate the constant part of the residual ----
+    for (int i = t; i < NY * HCS; i += DT) Hc[i] = 0.0;
+    mcp_eval_const_par(t, x, y, th, gh0);
+    __syncthreads();
+    for (int k = (t >> 5); k < NY; k += DT / 32)
+      for (int e = H_PTR[k] + (t & 31); e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+    __syncthreads();
+    bool parked = false;
+    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
+        parked = true;
+        break;
+      }
+      int inner = 1;  // :72
+      status = 0;     // :73
+      while (kkt > eps && inner < p.max_inner) {  // :75
+        // ---- direct part of C: G_x + tol·I, streamed from θ (the only per-step θ traffic) ----------------------
+        for (int c = t; c < NRED; c += DT) xt[c] = x[PERM[c]];
+        for (int d0 = t; d0 < ND; d0 += 4 * DT) {
+          int tp[4], t1[4], rc[4];
+          double acc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int d = min(d0 + u * DT, ND - 1);
+            tp[u] = D_TP[d];
+            t1[u] = D_TP[d + 1] & 0x7fffffff;
+            acc[u] = D_BASE[d] + ((tp[u] < 0) ? tol : 0.0);
+            rc[u] = D_ROW[d] * WS + D_CPOS[d];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            for (int q = tp[u] & 0x7fffffff; q < t1[u]; ++q) acc[u] += T_COEF[q] * opval(T_I[q].x, jv, th);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (d0 + u * DT < ND) W[rc[u]] = acc[u];
+        }
+        __syncthreads();
+        // ---- F (:79) from the affine structure: H = H(0) + H_x x,  G = G(0) + G_x x + G_y y,  G_y = −H_xᵀ ----------
+        if (t < NY) {
+          double a0 = 0.0, a1 = 0.0;
+          const double* hr = Hc + t * HCS;
+#pragma unroll 4
+          for (int c = 0; c + 1 < NRED; c += 2) {
+            a0 = fma(hr[c], xt[c], a0);
+            a1 = fma(hr[c + 1], xt[c + 1], a1);
+          }
+          if (NRED & 1) a0 = fma(hr[NRED - 1], xt[NRED - 1], a0);
+          w[t] = gh0[NX + t] + a0 + a1;
+        }
+        if (t >= 128 && t < 128 + NRED) {  // G in the NEW row ordering (row i ↔ old row PERM[i]); second half of the CTA
+          const int i = t - 128;
+          double a0 = gh0[PERM[i]] - tol * xt[i], a1 = 0.0;
+          const double* wr = W + i * WS;
+#pragma unroll 4
+          for (int c = 0; c < NRED; ++c) a0 = fma(wr[c], xt[c], a0);
+#pragma unroll 4
+          for (int k = 0; k < NY; ++k) a1 = fma(Hc[k * HCS + i], y[k], a1);
+          g[i] = a0 - a1;
+        }
+        __syncthreads();
+        double fmax_ = 0.0;
+        for (int i = t; i < NX; i += DT) fmax_ = nanmax(fmax_, fabs(g[i]));
+        for (int k = t; k < NY; k += DT) {
+          const double f2 = w[k] - s[k];
+          const double f3 = s[k] * y[k] - eps;
+          const double yt = y[k] + tol;
+          const double di = 1.0 / (tol + s[k] / yt);
+          dinv[k] = di;
+          w[k] = di * (-f2 - f3 / yt);
+          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+        }
+        const double kkt_new = blk_nanmax(fmax_, red, t);  // :107 (also orders the writes above)
+        // ---- right-hand side: −G − G_y w = −G + H_xᵀ w, into column NRED of W -----------------------------------
+        if (t < NRED) {
+          double a0 = -g[t];
+#pragma unroll 4
+          for (int k = 0; k < NY; ++k) a0 = fma(Hc[k * HCS + t], w[k], a0);
+          W[t * WS + NRED] = a0;
+        }
+        // ---- Schur part: C −= G_y D⁻¹ H_x = + H_xᵀ D⁻¹ H_x, register-tiled straight from the cached H_x -------------
+        {
+          double acc[DTR][DTR];
+#pragma unroll
+          for (int i = 0; i < DTR; ++i)
+#pragma unroll
+            for (int j = 0; j < DTR; ++j) acc[i][j] = 0.0;
+#pragma unroll 2
+          for (int k = 0; k < NY; ++k) {
+            const double dk = dinv[k];
+            const double* hr = Hc + k * HCS;
+            double av[DTR], bv[DTR];
+#pragma unroll
+            for (int i = 0; i < DTR; ++i) av[i] = hr[ti * DTR + i] * dk;
+#pragma unroll
+            for (int j = 0; j < DTR; ++j) bv[j] = hr[tj * DTR + j];
+#pragma unroll
+            for (int i = 0; i < DTR; ++i)
+#pragma unroll
+              for (int j = 0; j < DTR; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < DTR; ++i)
+#pragma unroll
+            for (int j = 0; j < DTR; ++j) {
+              const int r = ti * DTR + i, c = tj * DTR + j;
+              if (r < NRED && c < NRED) W[r * WS + c] += acc[i][j];
+            }
+          __syncthreads();
+        }
+        // ---- LU with partial pivoting, rows stay in place; forward substitution rides in column NRED -----------
+        bool failed = false;
+        {
+          bool done_row = false;  // my row has already been a pivot
+          constexpr int NPR = (NRED + 2) / 2;         // double2 pairs per row incl. the rhs column
+          constexpr int HP = (NPR + 1) / 2;           // pairs per column half
+          for (int j = 0; j < NRED; ++j) {
+            const double vj = (r_ < NRED) ? W[r_ * WS + j] : 0.0;
+            unsigned key = 0;
+            if (hf == 0 && r_ < NRED && !done_row)
+              key = ((unsigned)__double2hiint(fabs(vj)) & 0xffffff00u) | (unsigned)(255 - r_);
+            key = __reduce_max_sync(FULLMASK, key);
+            if ((t & 31) == 0) sh_key[t >> 5] = key;
+            __syncthreads();
+            unsigned best = sh_key[0];
+#pragma unroll
+            for (int i = 1; i < DT / 32; ++i) best = max(best, sh_key[i]);
+            const int pr = 255 - (int)(best & 0xffu);
+            const double piv = W[pr * WS + j];
+            if (best == 0 || !(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) {  // :84-88
+              failed = true;
+              break;
+            }
+            const double rp = 1.0 / piv;
+            if (t == 0) {
+              ord[j] = pr;
+              rd[j] = rp;
+            }
+            const double m = (r_ < NRED && !done_row && r_ != pr) ? -(vj * rp) : 0.0;
+            if (m != 0.0) {
+              const double2* Wp2 = reinterpret_cast<const double2*>(W + pr * WS);
+              double2* Wr2 = reinterpret_cast<double2*>(W + r_ * WS);
+              const int c0 = hf * HP, c1 = min(NPR, c0 + HP);
+#pragma unroll 4
+              for (int c = c0; c < c1; ++c) {
+                const double2 u = Wp2[c];
+                double2 a = Wr2[c];
+                a.x = fma(m, u.x, a.x);
+                a.y = fma(m, u.y, a.y);
+                Wr2[c] = a;
+              }
+            }
+            if (r_ == pr) done_row = true;
+            __syncthreads();
+          }
+        }
+        failed = __syncthreads_or(failed);
+        double a_s = 1.0, a_y = 1.0;
+        if (!failed) {
+          // ---- back substitution, column sweep over the pivot order ------------------------------------------------
+          for (int j = NRED - 1; j >= 0; --j) {
+            const int pr = ord[j];
+            const double xj = W[pr * WS + NRED] * rd[j];
+            if (t == 0) sol[j] = xj;
+            if (t < j) {
+              const int ri = ord[t];
+              W[ri * WS + NRED] = fma(-W[ri * WS + j], xj, W[ri * WS + NRED]);
+            }
+            __syncthreads();
+          }
+          // ---- δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol) ---------------------------------------------------
+          if (t < NY) {
+            double a0 = 0.0, a1 = 0.0;
+            const double* hr = Hc + t * HCS;
+#pragma unroll 4
+            for (int c = 0; c + 1 < NRED; c += 2) {
+              a0 = fma(hr[c], sol[c], a0);
+              a1 = fma(hr[c + 1], sol[c + 1], a1);
+            }
+            if (NRED & 1) a0 = fma(hr[NRED - 1], sol[NRED - 1], a0);
+            const double dy = w[t] - dinv[t] * (a0 + a1);
+            const double f3 = s[t] * y[t] - eps;
+            w[t] = dy;
+            dinv[t] = -(f3 + s[t] * dy) / (y[t] + tol);
+          }
+          __syncthreads();
+          a_s = blk_ftb_linesearch(s, dinv, p.min_stepsize, t);  // :93
+          a_y = blk_ftb_linesearch(y, w, p.min_stepsize, t);     // :94
+          failed = (a_s != a_s) || (a_y != a_y);                 // :96-100
+        }
+        if (failed) {
+          status = 1;
+          break;
+        }
+        for (int c = t; c < NRED; c += DT) x[PERM[c]] += a_s * sol[c];  // :103
+        for (int k = t; k < NY; k += DT) {
+          s[k] += a_s * dinv[k];                                        // :104
+          y[k] += a_y * w[k];                                           // :105
+        }
+        __syncthreads();
+        kkt = kkt_new;  // :107
+        ++inner;        // :108
+        ++steps;
+      }
+      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
+      ++outer;                                                                                              // :114
+    }
+    if (!parked && outer == p.max_outer) status = 1;  // :117-119
+    for (int i = t; i < NX; i += DT) p.x_out[inst * NX + i] = x[i];
+    for (int i = t; i < NY; i += DT) {
+      p.y_out[inst * NY + i] = y[i];
+      p.s_out[inst * NY + i] = s[i];
+    }
+    if (t == 0) {
+      p.kkt_out[inst] = kkt;
+      p.eps_out[inst] = eps;
+      p.outer_out[inst] = outer;
+      p.status_out[inst] = status;
+      p.steps_out[inst] = steps;
+      if (parked) {
+        p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+      } else {
+        atomicAdd(p.counters + 1, (unsigned long long)steps);
+        if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+      }
+    }
+  }
+}
+#else
+extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const SolveParams p) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  double* x = smem + DENSE_OFF_X;
+  double* y = smem + DENSE_OFF_Y;
+  double* s = smem + DENSE_OFF_S;
+  double* g = smem + DENSE_OFF_G;
+  double* w = smem + DENSE_OFF_W;        // H rows, then w, then δy
+  double* dinv = smem + DENSE_OFF_DINV;  // D⁻¹, then δs
+  double* sol = smem + DENSE_OFF_SOL;
+  double* jv = smem + DENSE_OFF_JV;      // computed Jacobian entries (none for the QP configs)
+  double* W = smem + DENSE_OFF_WIN;      // NRED rows × WS1 (column NRED = right-hand side)
+  double* gbs = smem + DENSE_OFF_STG;    // DKB × DNP : G_y[:, k]·D⁻¹_k
+  double* hbs = gbs + DKB * DNP;         // DKB × DNP : H_x[k, :]
+  double* part = smem + DENSE_OFF_PART;  // 2 × 128 partial sums
+  double* red = smem + DENSE_OFF_RED;    // 16 doubles of reduction scratch
+  double* rd = smem + DENSE_OFF_RD;      // reciprocal pivots
+  int* ord = reinterpret_cast<int*>(smem + DENSE_OFF_ORD);  // pivot row of each elimination step
+  __shared__ unsigned long long sh_q;
+  __shared__ unsigned sh_key[DT / 32];
+#if THETA_IN_SMEM
+  double* th = smem + DENSE_OFF_TH;
+#else
+  const double* th = p.theta;
+#endif
+  const double tol = p.tol;
+  constexpr int WS = WS1;
+  const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+  const int r_ = t & 127, hf = t >> 7;   // (row, column half) mapping of the factorisation
+  const int ti = t >> 4, tj = t & 15;    // 16×16 tile grid of the Schur update
+
+  for (;;) {
+    __syncthreads();
+    if (t == 0) sh_q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+    __syncthreads();
+    unsigned long long inst = sh_q;
+    if (p.pass) {
+      if (inst >= n_deferred) break;
+      inst = (unsigned long long)p.deferred[inst];
+    } else if (inst >= (unsigned long long)p.B) {
+      break;
+    }
+#if THETA_IN_SMEM
+    for (int i = t; i < NT; i += DT) th[i] = p.theta[inst * NT + i];
+#else
+    th = p.theta + inst * NT;
+#endif
+    double eps = 1.0;                                        // :67
+    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // :68
+    int status = 0, outer = 1, steps = 0;                    // :69-70
+    if (p.pass) {
+      for (int i = t; i < NX; i += DT) x[i] = p.x_out[inst * NX + i];
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y_out[inst * NY + i];
+        s[i] = p.s_out[inst * NY + i];
+      }
+      eps = p.eps_out[inst];
+      kkt = p.kkt_out[inst];
+      outer = p.outer_out[inst];
+      steps = p.steps_out[inst];
+    } else {
+      for (int i = t; i < NX; i += DT) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      }
+    }
+    __syncthreads();
+    bool parked = false;
+    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
+        parked = true;
+        break;
+      }
+      int inner = 1;  // :72
+      status = 0;     // :73
+      while (kkt > eps && inner < p.max_inner) {  // :75
+        // ---- F (:79): thread i evaluates generated part i; H lands in w -----------------------------------
+        mcp_eval_newton_par(t, x, y, th, g, w, jv);
+        __syncthreads();
+        double fmax_ = 0.0;
+        for (int i = t; i < NX; i += DT) fmax_ = nanmax(fmax_, fabs(g[i]));
+        for (int k = t; k < NY; k += DT) {
+          const double f2 = w[k] - s[k];
+          const double f3 = s[k] * y[k] - eps;
+          const double yt = y[k] + tol;
+          const double di = 1.0 / (tol + s[k] / yt);
+          dinv[k] = di;
+          w[k] = di * (-f2 - f3 / yt);
+          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+        }
+        const double kkt_new = blk_nanmax(fmax_, red, t);  // :107 (also orders the writes above)
+        // ---- right-hand side of the condensed system into column NRED of W ----------------------------------
+        {
+          double acc = 0.0;
+          if (r_ < NRED) {
+            const int e0 = R_PTR[r_], e1 = R_PTR[r_ + 1], mid = e0 + (e1 - e0 + 1) / 2;
+            for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
+          }
+          part[hf * 128 + r_] = acc;
+          __syncthreads();
+          if (t < NRED) W[t * WS + NRED] = -g[R_GROW[t]] - part[t] - part[128 + t];
+        }
+        // ---- direct part of C: G_x + tol·I (one dest per matrix entry, row-sorted) ---------------------------
+        for (int d = t; d < ND; d += DT) {
+          const int tp = D_TP[d];
+          const int t1 = D_TP[d + 1] & 0x7fffffff;
+          double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
+          for (int q = tp & 0x7fffffff; q < t1; ++q) acc += T_COEF[q] * opval(T_I[q].x, jv, th);
+          W[D_ROW[d] * WS + D_CPOS[d]] = acc;
+        }
+        // ---- Schur part: C −= Σ_k (G_y[:,k] D⁻¹_k) ⊗ H_x[k,:], register-tiled over blocks of DKB constraints ----
+        {
+          double acc[DTR][DTR];
+#pragma unroll
+          for (int i = 0; i < DTR; ++i)
+#pragma unroll
+            for (int j = 0; j < DTR; ++j) acc[i][j] = 0.0;
+          for (int k0 = 0; k0 < NY; k0 += DKB) {
+            __syncthreads();
+            for (int i = t; i < 2 * DKB * DNP; i += DT) gbs[i] = 0.0;
+            __syncthreads();
+            {
+              const int kk = t >> 5, k = k0 + kk, ln = t & 31;  // warp kk stages constraint k0+kk
+              if (k < NY) {
+                const double dk = dinv[k];
+                for (int e = H_PTR[k] + ln; e < H_PTR[k + 1]; e += 32) hbs[kk * DNP + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+                for (int e = GK_PTR[k] + ln; e < GK_PTR[k + 1]; e += 32) gbs[kk * DNP + GK_ROW[e]] = GK_COEF[e] * opval(GK_CODE[e], jv, th) * dk;
+              }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < DKB; ++kk) {
+              double av[DTR], bv[DTR];
+#pragma unroll
+              for (int i = 0; i < DTR; ++i) av[i] = gbs[kk * DNP + ti * DTR + i];
+#pragma unroll
+              for (int j = 0; j < DTR; ++j) bv[j] = hbs[kk * DNP + tj * DTR + j];
+#pragma unroll
+              for (int i = 0; i < DTR; ++i)
+#pragma unroll
+                for (int j = 0; j < DTR; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < DTR; ++i)
+#pragma unroll
+            for (int j = 0; j < DTR; ++j) {
+              const int r = ti * DTR + i, c = tj * DTR + j;
+              if (r < NRED && c < NRED) W[r * WS + c] -= acc[i][j];
+            }
+          __syncthreads();
+        }
+        // ---- LU with partial pivoting, rows stay in place; forward substitution rides in column NRED -----------
+        bool failed = false;
+        {
+          bool done_row = false;  // my row has already been a pivot
+          constexpr int NPR = (NRED + 2) / 2;         // double2 pairs per row incl. the rhs column
+          constexpr int HP = (NPR + 1) / 2;           // pairs per column half
+          for (int j = 0; j < NRED; ++j) {
+            const double vj = (r_ < NRED) ? W[r_ * WS + j] : 0.0;
+            unsigned key = 0;
+            if (hf == 0 && r_ < NRED && !done_row)
+              key = ((unsigned)__double2hiint(fabs(vj)) & 0xffffff00u) | (unsigned)(255 - r_);
+            key = __reduce_max_sync(FULLMASK, key);
+            if ((t & 31) == 0) sh_key[t >> 5] = key;
+            __syncthreads();
+            unsigned best = sh_key[0];
+#pragma unroll
+            for (int i = 1; i < DT / 32; ++i) best = max(best, sh_key[i]);
+            const int pr = 255 - (int)(best & 0xffu);
+            const double piv = W[pr * WS + j];
+            if (best == 0 || !(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) {  // :84-88
+              failed = true;
+              break;
+            }
+            const double rp = 1.0 / piv;
+            if (t == 0) {
+              ord[j] = pr;
+              rd[j] = rp;
+            }
+            const double m = (r_ < NRED && !done_row && r_ != pr) ? -(vj * rp) : 0.0;
+            if (m != 0.0) {
+              const double2* Wp2 = reinterpret_cast<const double2*>(W + pr * WS);
+              double2* Wr2 = reinterpret_cast<double2*>(W + r_ * WS);
+              const int c0 = hf * HP, c1 = min(NPR, c0 + HP);
+#pragma unroll 4
+              for (int c = c0; c < c1; ++c) {
+                const double2 u = Wp2[c];
+                double2 a = Wr2[c];
+                a.x = fma(m, u.x, a.x);
+                a.y = fma(m, u.y, a.y);
+                Wr2[c] = a;
+              }
+            }
+            if (r_ == pr) done_row = true;
+            __syncthreads();
+          }
+        }
+        failed = __syncthreads_or(failed);
+        double a_s = 1.0, a_y = 1.0;
+        if (!failed) {
+          // ---- back substitution, column sweep over the pivot order ------------------------------------------------
+          for (int j = NRED - 1; j >= 0; --j) {
+            const int pr = ord[j];
+            const double xj = W[pr * WS + NRED] * rd[j];
+            if (t == 0) sol[j] = xj;
+            if (t < j) {
+              const int ri = ord[t];
+              W[ri * WS + NRED] = fma(-W[ri * WS + j], xj, W[ri * WS + NRED]);
+            }
+            __syncthreads();
+          }
+          // ---- δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol) ---------------------------------------------------
+          {
+            double acc = 0.0;
+            if (r_ < NY) {
+              const int e0 = H_PTR[r_], e1 = H_PTR[r_ + 1], mid = e0 + (e1 - e0 + 1) / 2;
+              for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
+            }
+            part[hf * 128 + r_] = acc;
+            __syncthreads();
+            for (int k = t; k < NY; k += DT) {
+              const double dy = w[k] - dinv[k] * (part[k] + part[128 + k]);
+              const double f3 = s[k] * y[k] - eps;
+              w[k] = dy;
+              dinv[k] = -(f3 + s[k] * dy) / (y[k] + tol);
+            }
+            __syncthreads();
+          }
+          a_s = blk_ftb_linesearch(s, dinv, p.min_stepsize, t);  // :93
+          a_y = blk_ftb_linesearch(y, w, p.min_stepsize, t);     // :94
+          failed = (a_s != a_s) || (a_y != a_y);                 // :96-100
+        }
+        if (failed) {
+          status = 1;
+          break;
+        }
+        for (int c = t; c < NRED; c += DT) x[PERM[c]] += a_s * sol[c];  // :103
+        for (int k = t; k < NY; k += DT) {
+          s[k] += a_s * dinv[k];                                        // :104
+          y[k] += a_y * w[k];                                           // :105
+        }
+        __syncthreads();
+        kkt = kkt_new;  // :107
+        ++inner;        // :108
+        ++steps;
+      }
+      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
+      ++outer;                                                                                              // :114
+    }
+    if (!parked && outer == p.max_outer) status = 1;  // :117-119
+    for (int i = t; i < NX; i += DT) p.x_out[inst * NX + i] = x[i];
+    for (int i = t; i < NY; i += DT) {
+      p.y_out[inst * NY + i] = y[i];
+      p.s_out[inst * NY + i] = s[i];
+    }
+    if (t == 0) {
+      p.kkt_out[inst] = kkt;
+      p.eps_out[inst] = eps;
+      p.outer_out[inst] = outer;
+      p.status_out[inst] = status;
+      p.steps_out[inst] = steps;
+      if (parked) {
+        p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+      } else {
+        atomicAdd(p.counters + 1, (unsigned long long)steps);
+        if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+      }
+    }
+  }
+}
+#endif  // DENSE_KERNEL == 2
+#else   // !DENSE_KERNEL
 // ------------------------------------------------------------------------------------------------
 // The solve kernel: persistent CTAs; every sub-warp (SUB lanes) pulls instances from a global queue and
 // runs the reference's loop (src/solver.jl:63-121) as a small state machine, one Newton step per trip
@@ -780,6 +1401,8 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
     __syncwarp(smask);
   }
 }
+
+#endif  // DENSE_KERNEL
 
 // ------------------------------------------------------------------------------------------------
 // Sensitivity kernel: ∂z/∂θ = (−∇F_z)⁻¹ ∇F_θ at the returned point, no tol·I (src/AutoDiff.jl:18-40),

@@ -299,7 +299,9 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
 int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream_t stream) {
   const Plan& P = h->plan;
   const long long ctas_needed = (p.B + P.ipc_solve - 1) / P.ipc_solve;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(st->num_sms, ctas_needed));
+  const long long max_ctas = (long long)st->num_sms * (P.dense_kernel ? P.dense_ctas_per_sm : 1);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
+  const unsigned block = P.dense_kernel ? 256u : (unsigned)(P.sub * P.ipc_solve);
   const size_t scratch_bytes = (size_t)st->num_sms * P.ipc_solve * P.scratch_doubles_solve * 8;
   if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * P.ipc_sens * P.scratch_doubles_sens * 8)))
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
@@ -320,11 +322,11 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
   p.pass = 0;
-  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, (unsigned)(P.sub * P.ipc_solve), 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
   st->launches = 1;
   if (budget > 0) {
     p.pass = 1;
-    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, (unsigned)(P.sub * P.ipc_solve), 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
     st->launches = 2;
   }
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
@@ -457,9 +459,9 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->n_jac_constant = P.n_const_entries;
   info->n_assembly_dests = (int)P.d_row.size();
   info->n_assembly_terms = (int)P.t_coef.size();
-  info->threads_per_instance = P.sub;
+  info->threads_per_instance = P.dense_kernel ? 256 : P.sub;
   info->instances_per_cta = P.ipc_solve;
-  info->ctas_per_sm = 1;
+  info->ctas_per_sm = P.dense_kernel ? P.dense_ctas_per_sm : 1;
   info->smem_bytes_per_cta = (int)P.smem_solve;
   info->has_sensitivities = P.has_jt;
   info->cache_hit = h->cache_hit;

@@ -403,6 +403,104 @@ Operand classify(const Plan& P, int node, std::map<int, int>& slot_of_node, std:
   return {1.0, it->second};
 }
 
+
+// Substitute x = 0, y = 0 in the tape and fold constants: the residual's constant part G(0;θ), H(0;θ) of a
+// problem that is affine in z.  Returns a small tape (only θ leaves) and, per root, its node in that tape.
+struct ZeroTape {
+  Plan tape;                     // only op / a / b / consts are used (by Emitter)
+  std::vector<int32_t> roots;
+};
+
+ZeroTape substitute_zero(const Plan& P, const std::vector<int32_t>& roots) {
+  ZeroTape Z;
+  Plan& T = Z.tape;
+  const size_t n = P.op.size();
+  std::vector<char> is_c(n, 0);
+  std::vector<double> cval(n, 0.0);
+  std::vector<int32_t> node(n, -1);
+  std::map<double, int32_t> const_node;
+  auto mk_const = [&](double v) -> int32_t {
+    auto it = const_node.find(v);
+    if (it != const_node.end()) return it->second;
+    T.consts.push_back(v);
+    T.op.push_back(MCPB200_OP_CONST);
+    T.a.push_back((int32_t)T.consts.size() - 1);
+    T.b.push_back(-1);
+    return const_node[v] = (int32_t)T.op.size() - 1;
+  };
+  auto mk = [&](int op, int32_t a, int32_t b) -> int32_t {
+    T.op.push_back(op);
+    T.a.push_back(a);
+    T.b.push_back(b);
+    return (int32_t)T.op.size() - 1;
+  };
+  auto as_node = [&](size_t i) -> int32_t { return is_c[i] ? mk_const(cval[i]) : node[i]; };
+  std::vector<char> need(n, 0);
+  {
+    std::vector<int> st(roots.begin(), roots.end());
+    while (!st.empty()) {
+      int v = st.back();
+      st.pop_back();
+      if (need[v]) continue;
+      need[v] = 1;
+      if (is_binary(P.op[v])) { st.push_back(P.a[v]); st.push_back(P.b[v]); }
+      else if (!is_leaf(P.op[v])) st.push_back(P.a[v]);
+    }
+  }
+  for (size_t i = 0; i < n; ++i) {
+    if (!need[i]) continue;
+    const int op = P.op[i];
+    const int a = P.a[i], b = P.b[i];
+    auto setc = [&](double v) { is_c[i] = 1; cval[i] = v; };
+    switch (op) {
+      case MCPB200_OP_CONST: setc(P.consts[a]); break;
+      case MCPB200_OP_X: case MCPB200_OP_Y: setc(0.0); break;
+      case MCPB200_OP_THETA: node[i] = mk(MCPB200_OP_THETA, a, -1); break;
+      case MCPB200_OP_ADD:
+        if (is_c[a] && is_c[b]) setc(cval[a] + cval[b]);
+        else if (is_c[a] && cval[a] == 0.0) node[i] = node[b];
+        else if (is_c[b] && cval[b] == 0.0) node[i] = node[a];
+        else node[i] = mk(op, as_node(a), as_node(b));
+        break;
+      case MCPB200_OP_SUB:
+        if (is_c[a] && is_c[b]) setc(cval[a] - cval[b]);
+        else if (is_c[b] && cval[b] == 0.0) node[i] = node[a];
+        else if (is_c[a] && cval[a] == 0.0) node[i] = mk(MCPB200_OP_NEG, node[b], -1);
+        else node[i] = mk(op, as_node(a), as_node(b));
+        break;
+      case MCPB200_OP_MUL:
+        if (is_c[a] && is_c[b]) setc(cval[a] * cval[b]);
+        else if ((is_c[a] && cval[a] == 0.0) || (is_c[b] && cval[b] == 0.0)) setc(0.0);
+        else if (is_c[a] && cval[a] == 1.0) node[i] = node[b];
+        else if (is_c[b] && cval[b] == 1.0) node[i] = node[a];
+        else node[i] = mk(op, as_node(a), as_node(b));
+        break;
+      case MCPB200_OP_DIV:
+        if (is_c[a] && is_c[b]) setc(cval[a] / cval[b]);
+        else if (is_c[a] && cval[a] == 0.0) setc(0.0);
+        else if (is_c[b] && cval[b] == 1.0) node[i] = node[a];
+        else node[i] = mk(op, as_node(a), as_node(b));
+        break;
+      case MCPB200_OP_NEG:
+        if (is_c[a]) setc(-cval[a]); else node[i] = mk(op, node[a], -1);
+        break;
+      case MCPB200_OP_POWI:
+        if (is_c[a]) setc(std::pow(cval[a], (double)b)); else node[i] = mk(op, node[a], b);
+        break;
+      default:  // sqrt, exp, log, sin, cos
+        if (is_c[a]) {
+          const double v = cval[a];
+          setc(op == MCPB200_OP_SQRT ? std::sqrt(v) : op == MCPB200_OP_EXP ? std::exp(v) : op == MCPB200_OP_LOG ? std::log(v)
+               : op == MCPB200_OP_SIN ? std::sin(v) : std::cos(v));
+        } else {
+          node[i] = mk(op, node[a], -1);
+        }
+    }
+  }
+  for (int32_t r : roots) Z.roots.push_back(as_node(r));
+  return Z;
+}
+
 // smallest stride ≥ v with stride ≡ 2 (mod 4): rows are 16-byte aligned and lanes striding over rows hit
 // distinct 16-byte bank groups, so 128-bit shared-memory accesses are conflict free
 int stride_for(int v) {
@@ -566,6 +664,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       for (auto& t : kv.second) n_schur += (t.k >= 0);
     P.dense_schur = (P.R == N && P.WC == N && n_schur > 4 * dest.size()) ? 1 : 0;
     if (const char* e = getenv("MCPB200_DENSE_SCHUR")) P.dense_schur = (atoi(e) != 0) && P.R == N && P.WC == N;
+    P.dense_kernel = (P.dense_schur && N <= 112 && ny <= 128) ? 1 : 0;   // thread mappings of the dense kernel
+    if (const char* e = getenv("MCPB200_DENSE_KERNEL")) P.dense_kernel = (atoi(e) != 0) && P.dense_schur && N <= 112 && ny <= 128;
     if (P.dense_schur)
       for (auto& kv : dest) {
         auto& v = kv.second;
@@ -661,6 +761,26 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     }
   }
 
+  // ---- structure used by the dense kernel v2: G_y = −H_xᵀ (KKT structure), H_x independent of z ---------------
+  {
+    std::map<std::pair<int, int>, Operand> hx_map;
+    bool zconst = true;
+    for (auto& e : Hx) {
+      hx_map[{e.row, e.col}] = P.jz_opnd[e.idx];
+      if (P.jz_opnd[e.idx].code >= 0) zconst = false;
+    }
+    bool mhxt = Gy.size() == Hx.size();
+    for (auto& e : Gy) {
+      auto it = hx_map.find({e.col, e.row});
+      if (it == hx_map.end() || it->second.code != P.jz_opnd[e.idx].code || it->second.coef != -P.jz_opnd[e.idx].coef) {
+        mhxt = false;
+        break;
+      }
+    }
+    P.gy_is_mhxt = mhxt;
+    P.hx_zconst = zconst;
+    P.affine = P.jv_nodes.empty();   // every Jacobian entry is a constant or ±c·θ_i ⇒ G, H are affine in z
+  }
   // ---- shared-memory layout and launch configuration ---------------------------------------------------
   P.theta_in_smem = nt <= kThetaSmemMax ? 1 : 0;
   const int njv = (int)P.jv_nodes.size(), njtv = (int)P.jtv_nodes.size();
@@ -753,6 +873,50 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     P.ipc_sens = 1;
   }
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
+  if (P.dense_kernel) {
+    const int dtr = (N + 15) / 16, dnp = 16 * dtr;
+    off = 0;
+    place("DENSE_OFF_X", nx);
+    place("DENSE_OFF_Y", ny);
+    place("DENSE_OFF_S", ny);
+    place("DENSE_OFF_G", nx);
+    place("DENSE_OFF_W", ny);
+    place("DENSE_OFF_DINV", ny);
+    place("DENSE_OFF_SOL", N);
+    place("DENSE_OFF_JV", njv);
+    if (P.theta_in_smem) place("DENSE_OFF_TH", nt);
+    place("DENSE_OFF_WIN", (int64_t)N * P.WS1);
+    place("DENSE_OFF_STG", 2 * 8 * (int64_t)dnp);
+    place("DENSE_OFF_PART", 256);
+    place("DENSE_OFF_RED", 16);
+    place("DENSE_OFF_RD", N);
+    place("DENSE_OFF_ORD", (N + 1) / 2 + 1);
+    if (off * 8 > kSmemBudget) {
+      P.dense_kernel = 0;   // does not fit one CTA: stay on the general kernel
+    } else {
+      P.smem_solve = off * 8;
+      P.ipc_solve = 1;
+      P.dense_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(2, (kSmemBudget + 1024) / (off * 8 + 1024)));
+    }
+    // v2: H_x cached in shared memory for the whole solve, every mat-vec and the Schur complement from it
+    bool want_v2 = P.dense_kernel && P.gy_is_mhxt && P.hx_zconst && P.affine;
+    if (const char* e = getenv("MCPB200_DENSE_KERNEL")) want_v2 = want_v2 && atoi(e) >= 2;
+    if (want_v2) {
+      const int64_t hcs = (N + 1) | 1;   // odd row stride of the cached H_x
+      const int64_t off_v1 = off;
+      place("DENSE_OFF_HC", (int64_t)ny * hcs);
+      place("DENSE_OFF_XT", N);
+      place("DENSE_OFF_G0", nx + ny);
+      if (off * 8 <= kSmemBudget) {
+        P.dense_kernel = 2;
+        P.smem_solve = off * 8;
+        P.dense_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(2, (kSmemBudget + 1024) / (off * 8 + 1024)));
+        lay << "#define DENSE_HCS " << hcs << "\n";
+      } else {
+        off = off_v1;
+      }
+    }
+  }
   P.smem_sens = (shared_table_doubles + sens_doubles * P.ipc_sens) * 8;
   const int64_t cval_doubles = even(nd) + 2;
   P.scratch_doubles_solve = cval_doubles + even((int64_t)N * uts) + 2;
@@ -781,6 +945,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define UTS " << uts << "\n#define REGWIN " << P.regwin << "\n";
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
+  os << "#define DENSE_KERNEL " << P.dense_kernel << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
   os << lay.str();
@@ -791,6 +956,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     for (size_t i = 0; i < P.d_row.size(); ++i) rowptr[P.d_row[i] + 1]++;   // dests are sorted by row
     for (int i = 0; i < N; ++i) rowptr[i + 1] += rowptr[i];
     emit_table(os, "int", "D_ROWPTR", rowptr);
+    if (P.dense_kernel) emit_table(os, "int", "D_ROW", P.d_row);
     emit_table(os, "int", "D_CPOS", P.d_cpos);
     emit_table(os, "int", "D_TP", tp);
     emit_table(os, "double", "D_BASE", P.d_base, true);
@@ -836,7 +1002,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   Emitter E(P);
   // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
   os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
-  {
+  if (P.dense_kernel != 2) {
     std::vector<std::pair<int32_t, std::string>> outs;
     for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], "g[" + std::to_string(i) + "]"});
     for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], "h[" + std::to_string(i) + "]"});
@@ -844,7 +1010,18 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     E.partitioned(os, "mcp_eval_newton",
                   "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                   "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
-                  "x, y, th, g, h, jv", outs, P.sub);
+                  "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub);
+  }
+  if (P.dense_kernel == 2) {
+    os << "// G(0;θ), H(0;θ): the constant part of the (affine in z) residual\n";
+    ZeroTape Z = substitute_zero(P, P.gh_nodes);
+    Emitter EZ(Z.tape);
+    std::vector<std::pair<int32_t, std::string>> outs;
+    for (int i = 0; i < nx + ny; ++i) outs.push_back({Z.roots[i], "gh0[" + std::to_string(i) + "]"});
+    EZ.partitioned(os, "mcp_eval_const",
+                   "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                   "double* __restrict__ gh0",
+                   "x, y, th, gh0", outs, 256);
   }
   if (P.has_jt) {
     os << "// computed entries of ∇F_z and ∇F_θ at the solution (src/AutoDiff.jl:27-37)\n";

@@ -66,6 +66,9 @@ struct Plan {
   std::vector<double> h_coef;
   // G_y by column k (rows in the new ordering): dense Schur accumulation
   int dense_schur = 0;
+  int dense_kernel = 0;               // CTA-per-instance dense solve kernel (kernel_template.cuh, DENSE_KERNEL)
+  int dense_ctas_per_sm = 1;
+  bool gy_is_mhxt = false, hx_zconst = false, affine = false;   // structure flags (dense kernel v2)
   std::vector<int32_t> gk_ptr, gk_row, gk_code;
   std::vector<double> gk_coef;
   // θ-Jacobian, by column q: entries (row in [G;H], operand)
