@@ -179,11 +179,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lane_change")
-    ap.add_argument("--batch", type=int, default=1 << 18, help="θ columns per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="θ columns per GPU per step (default per workload)")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.batch is None:   # lane-change: 2^18 (tail of never-converging instances amortised); QP: θ is 161 KB/instance
+        args.batch = {"lane_change": 1 << 18, "readme_qp": 1 << 20, "random_qp": 1 << 13}.get(args.workload, 1 << 16)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -807,7 +807,6 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
         {
           bool done_row = false;  // my row has already been a pivot
           constexpr int NPR = (NRED + 2) / 2;         // double2 pairs per row incl. the rhs column
-          constexpr int HP = (NPR + 1) / 2;           // pairs per column half
           for (int j = 0; j < NRED; ++j) {
             const double vj = (r_ < NRED) ? W[r_ * WS + j] : 0.0;
             unsigned key = 0;
@@ -834,9 +833,10 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
             if (m != 0.0) {
               const double2* Wp2 = reinterpret_cast<const double2*>(W + pr * WS);
               double2* Wr2 = reinterpret_cast<double2*>(W + r_ * WS);
-              const int c0 = hf * HP, c1 = min(NPR, c0 + HP);
+              // columns < j are already zero in every unpivoted row: start at pair j/2; the two thread halves
+              // take alternate pairs so both stay busy as the active part shrinks
 #pragma unroll 4
-              for (int c = c0; c < c1; ++c) {
+              for (int c = (j >> 1) + hf; c < NPR; c += 2) {
                 const double2 u = Wp2[c];
                 double2 a = Wr2[c];
                 a.x = fma(m, u.x, a.x);
@@ -1080,7 +1080,6 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
         {
           bool done_row = false;  // my row has already been a pivot
           constexpr int NPR = (NRED + 2) / 2;         // double2 pairs per row incl. the rhs column
-          constexpr int HP = (NPR + 1) / 2;           // pairs per column half
           for (int j = 0; j < NRED; ++j) {
             const double vj = (r_ < NRED) ? W[r_ * WS + j] : 0.0;
             unsigned key = 0;
@@ -1107,9 +1106,10 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
             if (m != 0.0) {
               const double2* Wp2 = reinterpret_cast<const double2*>(W + pr * WS);
               double2* Wr2 = reinterpret_cast<double2*>(W + r_ * WS);
-              const int c0 = hf * HP, c1 = min(NPR, c0 + HP);
+              // columns < j are already zero in every unpivoted row: start at pair j/2; the two thread halves
+              // take alternate pairs so both stay busy as the active part shrinks
 #pragma unroll 4
-              for (int c = c0; c < c1; ++c) {
+              for (int c = (j >> 1) + hf; c < NPR; c += 2) {
                 const double2 u = Wp2[c];
                 double2 a = Wr2[c];
                 a.x = fma(m, u.x, a.x);

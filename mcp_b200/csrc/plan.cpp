@@ -921,10 +921,17 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   const int64_t cval_doubles = even(nd) + 2;
   P.scratch_doubles_solve = cval_doubles + even((int64_t)N * uts) + 2;
   P.scratch_doubles_sens = P.scratch_doubles_solve;
-  // banded LU with partial pivoting + forward/back substitution, dense-in-band count
+  // algorithmic flops of one Newton step's KKT solve: banded LU with partial pivoting +
+  // forward/back substitution, dense-in-band count; for dense plans ⅔n³ + 2n² plus the Schur product
+  // 2·Σ_k nnz(G_y[:,k])·nnz(H_x[k,:])
   {
     const double kl = P.kl, kuu = std::min(P.kl + P.ku, N - 1);
     P.flops_band = 2.0 * N * kl * kuu + 2.0 * N * kl + 2.0 * N * kuu;
+    if (P.dense_schur) {
+      double schur = 0.0;
+      for (int k = 0; k < ny; ++k) schur += 2.0 * (double)gy_by_k[k].size() * (double)hx_by_k[k].size();
+      P.flops_band = 2.0 / 3.0 * N * (double)N * N + 2.0 * N * (double)N + schur;
+    }
   }
 
   // ---- source ----------------------------------------------------------------------------------------------
