@@ -398,7 +398,7 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
 #pragma unroll
     for (int k = 0; k < CPW; ++k) {
       const int e = e0 + sl + SUB * k;
-      pre[k] = (e < e1) ? Cval[e] : 0.0;
+      pre[k] = (e < e1) ? __ldcg(Cval + e) : 0.0;   // written with st.cg: must not be served from a stale L1 line
     }
 
     // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, slot in the low byte ----

@@ -376,3 +376,26 @@ def test_lane_change_parity_statistics(lane_game):
           f"worst rel err among step-matched {worst:.2e}")
     assert same_status.mean() >= 0.995
     assert ok.mean() >= 0.99
+
+
+def test_in_library_multi_device_sharding(lane_game):
+    """`mcpb200_set_devices`: one host call, θ columns split in contiguous blocks over the GPUs of the box (one
+    host thread per device, no collective).  Results must be identical to the single-device run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs ≥ 2 GPUs (run under `gpurun --gpus 2`)")
+    from mcp_b200.solver import _handle
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(3001, seed=77)
+    h = _handle(mcp)
+    h.set_devices([0])
+    one = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    h.set_devices([0, 1])
+    two = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    t = h.timing()
+    h.set_devices([0])
+    np.testing.assert_array_equal(one.status, two.status)
+    np.testing.assert_array_equal(one.newton_steps, two.newton_steps)
+    np.testing.assert_array_equal(one.x, two.x)          # same kernel, same inputs ⇒ bit-identical
+    np.testing.assert_array_equal(one.y, two.y)
+    assert t["launches"] == 4 and t["solved"] == int((one.status == 0).sum())   # 2 passes on each of 2 devices
