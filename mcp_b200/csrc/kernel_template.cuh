@@ -122,24 +122,29 @@ __device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, doubl
                                                 const double* __restrict__ dinv, double tol, int sl, unsigned smask) {
   // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
 #if ASM_TWO_PHASE
-  // phase A, term-parallel (all table loads independent and coalesced): tmp[t] = coef·val(a)·[D⁻¹_k·val(b)]
+  // Two phases per chunk (chunks = runs of dests whose terms fit the shared term buffer):
+  //   A, term-parallel (all table loads independent and coalesced): tmp[t] = coef·val(a)·[D⁻¹_k·val(b)]
+  //   B, dest-parallel: sum the (contiguous) terms of each dest
+#pragma unroll 1
+  for (int c = 0; c < ASM_NCHUNK; ++c) {
+    const int tb = CH_T[c], te = CH_T[c + 1];
 #pragma unroll 4
-  for (int t = sl; t < NTERMS; t += SUB) {
-    const int4 ti = T_I[t];  // {a, b, k, -}
-    double v = T_COEF[t] * opval(ti.x, jv, th);
-    if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
-    tmp[t] = v;
+    for (int t = tb + sl; t < te; t += SUB) {
+      const int4 ti = T_I[t];  // {a, b, k, -}
+      double v = T_COEF[t] * opval(ti.x, jv, th);
+      if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
+      tmp[t - tb] = v;
+    }
+    __syncwarp(smask);
+    for (int d = CH_D[c] + sl; d < CH_D[c + 1]; d += SUB) {
+      const int tp = D_TP[d];
+      const int t1 = D_TP[d + 1] & 0x7fffffff;
+      double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
+      for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t - tb];
+      __stcg(Cval + d, acc);   // streaming scratch: keep L1 for the assembly tables
+    }
+    __syncwarp(smask);
   }
-  __syncwarp(smask);
-  // phase B, dest-parallel: sum the (contiguous) terms of each dest
-  for (int d = sl; d < ND; d += SUB) {
-    const int tp = D_TP[d];
-    const int t1 = D_TP[d + 1] & 0x7fffffff;
-    double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
-    for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t];
-    __stcg(Cval + d, acc);   // streaming scratch: keep L1 for the assembly tables
-  }
-  __syncwarp(smask);
 #else
   for (int d = sl; d < ND; d += SUB) {
     const int tp = D_TP[d];

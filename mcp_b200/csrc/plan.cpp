@@ -17,6 +17,7 @@ namespace {
 constexpr int kMaxWindowRows = 256;     // pivot key keeps the slot in 8 bits (kernel_template.cuh)
 constexpr int kMaxSensRhs = 16;
 constexpr int kSmemBudget = 227 * 1024; // bytes per CTA on sm_100a
+constexpr int kAsmChunk = 200;        // terms per chunk of the two-phase assembly (sizes the shared term buffer)
 constexpr int kThetaSmemMax = 512;      // θ longer than this is read from global memory in place
 
 bool is_binary(int op) { return op >= MCPB200_OP_ADD && op <= MCPB200_OP_DIV; }
@@ -815,7 +816,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     if (!regwin) return (int64_t)P.R * ws;
     int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
     w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
-    if (nterms_all <= 1024) w = std::max(w, nterms_all);                    // two-phase assembly buffer
+    w = std::max<int64_t>(w, std::min<int64_t>(nterms_all, kAsmChunk));     // two-phase assembly buffer (chunked)
     if (nx <= 1024) w = std::max<int64_t>(w, nx);                          // G alias
     return w;
   };
@@ -948,7 +949,31 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   {
     const int64_t win1 = win_solve, wins = win_sens, nterms = (int64_t)P.t_coef.size();
     // the window's storage doubles as the term buffer of the two-phase assembly and as the cp.async ring
-    os << "#define NTERMS " << nterms << "\n#define ASM_TWO_PHASE " << ((nterms <= std::min(win1, wins)) ? 1 : 0) << "\n";
+    // two-phase assembly in chunks: consecutive dests whose terms fit the shared term buffer
+    const int64_t buf = std::min(win1, wins);
+    std::vector<int32_t> ch_d, ch_t;   // chunk c covers dests [ch_d[c], ch_d[c+1]) and terms [ch_t[c], ch_t[c+1])
+    bool two_phase = nterms > 0;
+    ch_d.push_back(0);
+    ch_t.push_back(0);
+    for (size_t d0 = 0; d0 < P.d_row.size() && two_phase;) {
+      size_t d1 = d0;
+      while (d1 < P.d_row.size() && P.d_tptr[d1 + 1] - P.d_tptr[d0] <= buf) ++d1;
+      if (d1 == d0) {   // a single dest with more terms than the buffer: fall back to the one-phase loop
+        two_phase = false;
+        break;
+      }
+      ch_d.push_back((int32_t)d1);
+      ch_t.push_back(P.d_tptr[d1]);
+      d0 = d1;
+    }
+    if (!two_phase) {
+      ch_d.assign(1, 0);
+      ch_t.assign(1, 0);
+    }
+    os << "#define NTERMS " << nterms << "\n#define ASM_TWO_PHASE " << (two_phase ? 1 : 0) << "\n#define ASM_NCHUNK "
+       << (ch_d.size() - 1) << "\n";
+    emit_table(os, "int", "CH_D", ch_d);
+    emit_table(os, "int", "CH_T", ch_t);
     os << "#define UTS " << uts << "\n#define REGWIN " << P.regwin << "\n";
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
