@@ -24,6 +24,14 @@
 //   H_PTR H_CODE H_COL H_COEF (H_x rows), PERM, Q_PTR Q_ROW Q_CODE Q_COEF (θ-Jacobian by column)
 
 #define FULLMASK 0xffffffffu
+// State vectors are re-written during the kernel.  In shared memory `__restrict__` is a pure aliasing hint; once
+// they live in global memory (LARGE_STATE) `const T* __restrict__` would licence the non-coherent read-only path
+// (ld.global.nc) and stale reads, so the qualifier is dropped there.
+#if LARGE_STATE
+#define RS
+#else
+#define RS __restrict__
+#endif
 #ifndef SUB
 #define SUB 32  // lanes per instance
 #endif
@@ -44,6 +52,7 @@ struct SolveParams {
   int* status_out;
   int* steps_out;
   double* scratch;
+  double* state;                 // LARGE_STATE: per-instance vectors (global, L2-resident)
   unsigned long long* counters;  // [0] work queue, [1] Σ newton steps, [2] # solved, [3] # deferred, [4] pass-1 queue
   int* deferred;                 // instance ids handed from pass 0 to pass 1
   double tol;
@@ -69,11 +78,12 @@ struct SensParams {
   double* z_p;             // [n x P x B] or null
   int* status_out;         // or null
   double* scratch;
+  double* state;           // LARGE_STATE: per-instance vectors (global)
   unsigned long long* counters;
   int P;
 };
 
-__device__ __forceinline__ double opval(int code, const double* __restrict__ jv, const double* __restrict__ th) {
+__device__ __forceinline__ double opval(int code, const double* RS jv, const double* RS th) {
   return code >= 0 ? jv[code] : (code == -1 ? 1.0 : th[-2 - code]);
 }
 
@@ -117,9 +127,9 @@ __device__ __forceinline__ void load_shared_tables(double* smem_base) {
 // Assembly of the condensed matrix C = G_x + tol·I − G_y D⁻¹ H_x: one value per structural non-zero
 // ("dest", sorted by row then column) into the compact L2-resident array Cval[ND].
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void assemble_matrix(double* __restrict__ Cval, double* __restrict__ tmp,
-                                                const double* __restrict__ jv, const double* __restrict__ th,
-                                                const double* __restrict__ dinv, double tol, int sl, unsigned smask) {
+__device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
+                                                const double* RS jv, const double* RS th,
+                                                const double* RS dinv, double tol, int sl, unsigned smask) {
   // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
 #if ASM_TWO_PHASE
   // Two phases per chunk (chunks = runs of dests whose terms fit the shared term buffer):
@@ -189,10 +199,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // src/solver.jl:84-88).
 // ------------------------------------------------------------------------------------------------
 template <int NRHS, int WS>
-__device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cval, double* __restrict__ UT,
-                          double* __restrict__ sol, const int* __restrict__ rowptr,
-                          const unsigned short* __restrict__ cpos, const double* __restrict__ jv,
-                          const double* __restrict__ th, const double* __restrict__ dinv, double* __restrict__ stage,
+__device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
+                          double* RS sol, const int* RS rowptr,
+                          const unsigned short* RS cpos, const double* RS jv,
+                          const double* RS th, const double* RS dinv, double* RS stage,
                           int sl, unsigned smask) {
   constexpr int CPW = (WC + SUB - 1) / SUB;  // matrix positions per sl
   constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
@@ -566,7 +576,7 @@ __device__ int band_solve(double* __restrict__ W, const double* __restrict__ Cva
 }
 
 // `fraction_to_the_boundary_linesearch` — src/solver.jl:127-138, literally (τ = 0.995, decay = 0.5).
-__device__ __forceinline__ double ftb_linesearch(const double* __restrict__ v, const double* __restrict__ d,
+__device__ __forceinline__ double ftb_linesearch(const double* RS v, const double* RS d,
                                                  double min_step, int sl, unsigned smask) {
   const double c = 1.0 - 0.995;
   double alpha = 1.0;
@@ -610,7 +620,7 @@ __device__ __forceinline__ double blk_nanmax(double v, double* red, int t) {
 }
 
 // `fraction_to_the_boundary_linesearch` (src/solver.jl:127-138) with the whole CTA
-__device__ __forceinline__ double blk_ftb_linesearch(const double* __restrict__ v, const double* __restrict__ d,
+__device__ __forceinline__ double blk_ftb_linesearch(const double* RS v, const double* RS d,
                                                      double min_step, int t) {
   const double c = 1.0 - 0.995;
   double alpha = 1.0;
@@ -1215,17 +1225,23 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
   load_shared_tables(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
-  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SOLVE_SMEM_DOUBLES;
+  double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SOLVE_SMEM_DOUBLES;  // my shared-memory block
+#if LARGE_STATE
+  double* S = p.state + ((size_t)blockIdx.x * SOLVE_INST + slot) * SOLVE_STATE_DOUBLES;  // vectors in global memory
+  double* W = V;                                                                         // only the window is shared
+#else
+  double* S = V;
+  double* W = V + SOLVE_OFF_WIN;
+#endif
   double* x = S + SOLVE_OFF_X;
   double* y = S + SOLVE_OFF_Y;
   double* s = S + SOLVE_OFF_S;
-  double* g = S + SOLVE_OFF_G;        // G rows (aliases the window when it fits)
+  double* g = SOLVE_G_IN_WIN ? W : S + SOLVE_OFF_G;  // G rows (alias the window region when they fit)
   double* hh = S + SOLVE_OFF_H;       // H rows (alias w: H[k] is consumed where w[k] is produced)
   double* jv = S + SOLVE_OFF_JV;
   double* dinv = S + SOLVE_OFF_DINV;  // D⁻¹, later δs
   double* w = S + SOLVE_OFF_W;        // w, later δy
   double* sol = S + SOLVE_OFF_SOL;    // δx in the permuted ordering
-  double* W = S + SOLVE_OFF_WIN;
 #if THETA_IN_SMEM
   double* th = S + SOLVE_OFF_TH;
 #else
@@ -1422,7 +1438,14 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
   load_shared_tables(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
-  double* S = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SENS_SMEM_DOUBLES;
+  double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SENS_SMEM_DOUBLES;
+#if LARGE_STATE
+  double* S = p.state + ((size_t)blockIdx.x * SENS_INST + slot) * SENS_STATE_DOUBLES;
+  double* W = V;
+#else
+  double* S = V;
+  double* W = V + SENS_OFF_WIN;
+#endif
   double* x = S + SENS_OFF_X;
   double* y = S + SENS_OFF_Y;
   double* s = S + SENS_OFF_S;
@@ -1431,7 +1454,6 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
   double* dinv = S + SENS_OFF_DINV;
   double* wq = S + SENS_OFF_WQ;    // [NRHS_SENS][NY]
   double* sol = S + SENS_OFF_SOL;  // [NRHS_SENS][NRED]
-  double* W = S + SENS_OFF_WIN;
 #if THETA_IN_SMEM
   double* th = S + SENS_OFF_TH;
 #endif

@@ -43,6 +43,7 @@ struct SolveParams {
   double *x_out, *y_out, *s_out, *kkt_out, *eps_out;
   int *outer_out, *status_out, *steps_out;
   double* scratch;
+  double* state;
   unsigned long long* counters;
   int* deferred;
   double tol, tightening_rate, loosening_rate, min_stepsize;
@@ -59,6 +60,7 @@ struct SensParams {
   double* z_p;
   int* status_out;
   double* scratch;
+  double* state;
   unsigned long long* counters;
   int P;
 };
@@ -132,12 +134,13 @@ struct DeviceState {
   CUmodule mod = nullptr;
   CUfunction f_solve = nullptr, f_sens = nullptr;
   int num_sms = 0, regs_solve = 0, regs_sens = 0;
-  DevBuf scratch, counters, deferred, steps_tmp;
+  DevBuf scratch, state, counters, deferred, steps_tmp;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h1 = nullptr;
   cudaStream_t stream = nullptr;
   // staging buffers of the host entry points
   DevBuf theta, x, y, s, kkt, eps, outer, status, steps, big0, big1, big2, big3;
   bool timed = false;
+  bool pending = false;   // ev1 marks the end of the last enqueued launch sequence on this device
   long long launches = 0;
 };
 
@@ -307,6 +310,13 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
+  p.state = nullptr;
+  if (P.large_state) {
+    if (st->state.ensure((size_t)st->num_sms * std::max((size_t)P.ipc_solve * P.state_doubles_solve,
+                                                        (size_t)P.ipc_sens * P.state_doubles_sens) * 8 + 64))
+      return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(state) failed");
+    p.state = (double*)st->state.p;
+  }
   // two-pass scheduling (kernel_template.cuh): pass 0 parks instances that exceed the step budget, pass 1
   // resumes them together.  MCPB200_PASS1_STEPS overrides the budget (0 disables the second pass).
   int budget = 2 * std::max(p.max_inner, 1) + 24;
@@ -318,6 +328,9 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
     p.steps_out = (int*)st->steps_tmp.p;
   }
   p.step_budget = budget;
+  // Scratch, queue counters, deferred list and state block are per (handle, device): a sequence enqueued on
+  // another stream (e.g. torch's, by the _device entry points) must finish before this one may reuse them.
+  if (st->pending) CUDA_TRY(h, cudaStreamWaitEvent(stream, st->ev1, 0));
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
@@ -331,6 +344,7 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   }
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
   st->timed = true;
+  st->pending = true;
   return MCPB200_OK;
 }
 
@@ -343,12 +357,21 @@ int launch_sens(mcpb200_problem* h, DeviceState* st, SensParams& p, cudaStream_t
   if (st->scratch.ensure(scratch_bytes)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
+  p.state = nullptr;
+  if (P.large_state) {
+    if (st->state.ensure((size_t)st->num_sms * std::max((size_t)P.ipc_solve * P.state_doubles_solve,
+                                                        (size_t)P.ipc_sens * P.state_doubles_sens) * 8 + 64))
+      return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(state) failed");
+    p.state = (double*)st->state.p;
+  }
+  if (st->pending) CUDA_TRY(h, cudaStreamWaitEvent(stream, st->ev1, 0));
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
   CU_TRY(h, driver().LaunchKernel(st->f_sens, grid, 1, 1, (unsigned)(P.sub * P.ipc_sens), 1, 1, (unsigned)P.smem_sens, (CUstream)stream, args, nullptr));
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
   st->timed = true;
+  st->pending = true;
   st->launches = 1;
   return MCPB200_OK;
 }
@@ -423,7 +446,7 @@ int mcpb200_destroy(mcpb200_handle h) {
   for (auto& kv : h->dev) {
     DeviceState* st = kv.second.get();
     if (cudaSetDevice(st->dev) != cudaSuccess) continue;
-    for (DevBuf* b : {&st->scratch, &st->counters, &st->deferred, &st->steps_tmp, &st->theta, &st->x, &st->y, &st->s, &st->kkt, &st->eps, &st->outer,
+    for (DevBuf* b : {&st->scratch, &st->state, &st->counters, &st->deferred, &st->steps_tmp, &st->theta, &st->x, &st->y, &st->s, &st->kkt, &st->eps, &st->outer,
                       &st->status, &st->steps, &st->big0, &st->big1, &st->big2, &st->big3})
       b->release();
     for (cudaEvent_t e : {st->ev0, st->ev1, st->ev_h2d0, st->ev_h2d1, st->ev_d2h1})

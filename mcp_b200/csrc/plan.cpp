@@ -836,9 +836,11 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
   const int64_t stage_n = even(N);
   place("SOLVE_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
-  if (g_alias) lay << "#define SOLVE_OFF_G " << off << "\n";
+  const int64_t solve_state = off;     // everything above is "state"; the window region follows
+  if (g_alias) lay << "#define SOLVE_OFF_G 0\n";
+  lay << "#define SOLVE_G_IN_WIN " << (g_alias ? 1 : 0) << "\n";
   place("SOLVE_OFF_WIN", win_solve);
-  const int64_t solve_doubles = off;
+  int64_t solve_doubles = off;
   off = 0;
   place("SENS_OFF_X", nx);
   place("SENS_OFF_Y", ny);
@@ -850,8 +852,9 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
   if (P.theta_in_smem) place("SENS_OFF_TH", nt);
   place("SENS_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
+  const int64_t sens_state = off;
   place("SENS_OFF_WIN", win_sens);
-  const int64_t sens_doubles = off;
+  int64_t sens_doubles = off;
   const int64_t nd = (int64_t)P.d_row.size();
   const int64_t shared_table_doubles = even(((int64_t)(N + 1) * 4 + nd * 2 + 7) / 8);
   auto warps_for = [&](int64_t doubles) {  // instances per CTA
@@ -860,8 +863,26 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     if (P.sub == 16) w &= ~int64_t(1);       // whole warps
     return (int)std::max<int64_t>(0, w);
   };
+  // Large-state mode: when one instance's vectors do not fit shared memory next to the window (e.g. the masked
+  // game at N = 10: nx = 3000, ny = 3630), the iterate / residual / step vectors live in an L2-resident global
+  // block per instance and only the factorisation window stays in shared memory.  MCPB200_LARGE_STATE=1 forces it.
+  P.large_state = 0;
+  if (!P.dense_kernel) {
+    if (warps_for(solve_doubles) < 1 || (P.has_jt && warps_for(sens_doubles) < 1)) P.large_state = 1;
+    if (const char* e = getenv("MCPB200_LARGE_STATE")) P.large_state = atoi(e) != 0;
+  }
+  if (P.large_state) {
+    solve_doubles = even(win_solve);
+    sens_doubles = even(win_sens);
+    P.state_doubles_solve = even(solve_state) + 2;
+    P.state_doubles_sens = even(sens_state) + 2;
+  }
   P.ipc_solve = warps_for(solve_doubles);
   P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
+  if (P.large_state) {   // state traffic goes through L1/L2: a few warps per SM are enough to cover it
+    P.ipc_solve = std::min(P.ipc_solve, 8);
+    P.ipc_sens = std::min(P.ipc_sens, 8);
+  }
   if (P.ipc_solve < 1) {
     char buf[200];
     snprintf(buf, sizeof buf, "per-instance working set (%lld bytes) exceeds the %d-byte shared memory of one SM",
@@ -977,7 +998,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define UTS " << uts << "\n#define REGWIN " << P.regwin << "\n";
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
-  os << "#define DENSE_KERNEL " << P.dense_kernel << "\n";
+  os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
+  os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
   os << lay.str();
@@ -1040,8 +1062,9 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], "h[" + std::to_string(i) + "]"});
     for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], "jv[" + std::to_string(i) + "]"});
     E.partitioned(os, "mcp_eval_newton",
-                  "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
-                  "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
+                  P.large_state ? "const double* x, const double* y, const double* th, double* g, double* h, double* jv"
+                                : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                                  "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
                   "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub);
   }
   if (P.dense_kernel == 2) {
@@ -1064,8 +1087,9 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       os << "__device__ __forceinline__ void mcp_eval_sens_par(int, const double*, const double*, const double*, double*, double*) {}\n";
     } else {
       E.partitioned(os, "mcp_eval_sens",
-                    "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
-                    "double* __restrict__ jv, double* __restrict__ jtv",
+                    P.large_state ? "const double* x, const double* y, const double* th, double* jv, double* jtv"
+                                  : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                                    "double* __restrict__ jv, double* __restrict__ jtv",
                     "x, y, th, jv, jtv", outs, P.sub);
     }
   }

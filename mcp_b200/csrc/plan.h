@@ -65,6 +65,8 @@ struct Plan {
   std::vector<int32_t> h_ptr, h_code, h_col;
   std::vector<double> h_coef;
   // G_y by column k (rows in the new ordering): dense Schur accumulation
+  int large_state = 0;                // per-instance vectors in a global block, only the window in shared memory
+  int64_t state_doubles_solve = 0, state_doubles_sens = 0;
   int dense_schur = 0;
   int dense_kernel = 0;               // CTA-per-instance dense solve kernel (kernel_template.cuh, DENSE_KERNEL)
   int dense_ctas_per_sm = 1;
