@@ -334,15 +334,38 @@ struct Emitter {
   // group i, so the residual / Jacobian evaluation of one instance is spread over the warp.  Sub-expressions
   // shared between groups are recomputed per group.
   // outs[i] = {root node, "target[index]"}.
+  // smallest x-leaf (else nx + smallest y-leaf) each node depends on: a locality key — outputs of the same stage of
+  // a trajectory problem share sub-expressions, and a group recomputes whatever it shares with other groups
+  std::vector<int32_t> locality_keys() const {
+    const int32_t big = 1 << 30;
+    std::vector<int32_t> key(P.op.size(), big);
+    for (size_t n = 0; n < P.op.size(); ++n) {
+      const int op = P.op[n];
+      if (op == MCPB200_OP_X) key[n] = P.a[n];
+      else if (op == MCPB200_OP_Y) key[n] = P.nx + P.a[n];
+      else if (is_binary(op)) key[n] = std::min(key[P.a[n]], key[P.b[n]]);
+      else if (!is_leaf(op)) key[n] = key[P.a[n]];
+    }
+    return key;
+  }
+
   void partitioned(std::ostringstream& os, const std::string& name, const std::string& params,
-                   const std::string& args, const std::vector<std::pair<int32_t, std::string>>& outs,
+                   const std::string& args, std::vector<std::pair<int32_t, std::string>> outs,
                    int max_parts) const {
+    {
+      const std::vector<int32_t> key = locality_keys();
+      std::stable_sort(outs.begin(), outs.end(), [&](const auto& a, const auto& b) { return key[a.first] < key[b.first]; });
+    }
     std::vector<int32_t> roots;
     for (auto& o : outs) roots.push_back(o.first);
     const std::vector<int> cost = incremental_cost(roots);
     long total = 0;
     for (int c : cost) total += c;
-    const int K = (int)std::max<long>(1, std::min<long>(max_parts, std::min<long>((long)outs.size(), total / 24 + 1)));
+    // at most one part per lane while parts stay small; beyond ~kPartNodes tape nodes per part ptxas time explodes
+    // (superlinear in function size), so big problems get more parts and every lane loops over several
+    constexpr long kPartNodes = 600;
+    const long by_lanes = std::min<long>(max_parts, total / 24 + 1);
+    const int K = (int)std::max<long>(1, std::min<long>((long)outs.size(), std::max<long>(by_lanes, (total + kPartNodes - 1) / kPartNodes)));
     std::vector<size_t> begin(K + 1, outs.size());
     begin[0] = 0;
     {
@@ -360,7 +383,8 @@ struct Emitter {
       for (size_t i = begin[k]; i < begin[k + 1]; ++i) os << "  " << outs[i].second << " = " << operand(outs[i].first) << ";\n";
       os << "}\n";
     }
-    os << "__device__ __forceinline__ void " << name << "_par(int lane, " << params << ") {\n  switch (lane) {\n";
+    os << "__device__ __forceinline__ void " << name << "_par(int lane, " << params << ") {\n";
+    os << "#pragma unroll 1\n  for (int part = lane; part < " << K << "; part += " << max_parts << ")\n  switch (part) {\n";
     for (int k = 0; k < K; ++k) os << "    case " << k << ": " << name << "_p" << k << "(" << args << "); break;\n";
     os << "    default: break;\n  }\n}\n";
   }

@@ -133,3 +133,35 @@ def test_solve_argument_validation(readme_mcp):
         solve(InteriorPoint(), readme_mcp, np.zeros(2), linear_solve_algorithm="KLU")
     with pytest.raises(TypeError):
         solve(object(), readme_mcp, np.zeros(2))
+
+
+def _macros(src):
+    import re
+    return dict(re.findall(r"^#define (\w+) (-?\d+)$", src, flags=re.M))
+
+
+def test_plan_variants_are_selected_and_compile(monkeypatch, tmp_path):
+    """The planner picks a kernel family per problem structure; every family must compile for sm_100a."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    # banded trajectory game: register-resident window, one warp per instance
+    m = _macros(capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY).source())
+    assert (m["REGWIN"], m["SUB"], m["DENSE_KERNEL"], m["LARGE_STATE"]) == ("1", "32", "0", "0")
+    assert int(m["KL"]) <= 12 and int(m["WR"]) <= 13          # annealed ordering (RCM alone gives 17)
+    # tiny QP: two instances per warp
+    m = _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())
+    assert (m["SUB"], m["DENSE_KERNEL"]) == ("16", "0")
+    # dense QP with G_y = −H_xᵀ and an affine residual: CTA-per-instance kernel with H_x cached per solve
+    h = capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY)
+    m = _macros(h.source())
+    assert (m["DENSE_KERNEL"], m["DENSE_SCHUR"]) == ("2", "1") and h.info()["threads_per_instance"] == 256
+    assert "mcp_eval_const_par" in h.source() and "mcp_eval_newton_p0" not in h.source()
+    # the same problem with the v2 structure requirements switched off falls back to v1, then to the window kernel
+    monkeypatch.setenv("MCPB200_DENSE_KERNEL", "1")
+    assert _macros(capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY).source())["DENSE_KERNEL"] == "1"
+    monkeypatch.setenv("MCPB200_DENSE_KERNEL", "0")
+    assert _macros(capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY).source())["DENSE_KERNEL"] == "0"
+    monkeypatch.delenv("MCPB200_DENSE_KERNEL")
+    # large-state mode (vectors in global memory) can be forced on any banded problem
+    monkeypatch.setenv("MCPB200_LARGE_STATE", "1")
+    h = capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["LARGE_STATE"] == "1" and h.info()["smem_bytes_per_cta"] < 64 * 1024
