@@ -603,7 +603,11 @@ __device__ __forceinline__ double ftb_linesearch(const double* RS v, const doubl
 //     substitution.
 // The solver logic is the same literal restatement of src/solver.jl:63-121 as in mcp_solve_kernel.
 // ------------------------------------------------------------------------------------------------
+#if DENSE_KERNEL == 3
+#define DT 512
+#else
 #define DT 256
+#endif
 #define DKB 8
 #define DTR ((NRED + 15) / 16)  // register tile edge
 #define DNP (16 * DTR)          // padded dimension of the staged vectors
@@ -634,7 +638,390 @@ __device__ __forceinline__ double blk_ftb_linesearch(const double* RS v, const d
   return __longlong_as_double(0x7ff8000000000000LL);
 }
 
-#if DENSE_KERNEL == 2
+#if DENSE_KERNEL == 3
+// ------------------------------------------------------------------------------------------------
+// Dense kernel v3: the condensed matrix never touches shared memory.  One CTA of 16 warps per instance;
+// lane l owns rows {l, l+32, …} (D3_RCH chunks), warp w owns columns {w, w+16, …} (D3_CPW of them, the
+// right-hand side is column NRED), so every thread keeps a D3_RCH × D3_CPW tile of C in registers from the
+// Schur accumulation through the whole factorisation:
+//   * (G_x + tol·I)ᵀ (θ-only for these plans) is built once per solve into an L2-resident global block and
+//     loaded coalesced into the tiles each Newton step;  + H_xᵀ D⁻¹ H_x is accumulated on top from the
+//     cached H_x (4 conflict-free + 7 broadcast shared loads per 28 DFMAs);
+//   * LU with partial pivoting, one __syncthreads per column: column j lives entirely in warp j mod 16, which
+//     finds the pivot with one warp-wide max, and publishes the pivot row index and the multipliers; after the
+//     barrier every warp fetches its part of the pivot row by shuffle from lane (pivot row mod 32) and updates
+//     its columns > j (finished columns are skipped warp-uniformly).  Each warp also stores its part of the U
+//     row, transposed and in pivot order;
+//   * back substitution is a column sweep by warp 0 alone with the right-hand side in registers (no barriers).
+// The solver logic is the same literal restatement of src/solver.jl:63-121 as in mcp_solve_kernel.
+// ------------------------------------------------------------------------------------------------
+#define D3_RCH ((NRED + 31) / 32)
+#define D3_CPW ((NRED + 1 + 15) / 16)
+#define D3_CPN ((NRED + 15) / 16)
+#define D3_GLD 128
+// Keeps a select chain over tile registers from being rewritten as a dynamically indexed (local-memory) load.
+__device__ __forceinline__ double d3_opaque(double v) {
+  asm("" : "+d"(v));
+  return v;
+}
+
+// 16 elimination steps (columns 16·AJ … 16·AJ+15) of the register-resident LU; AJ is a template parameter so
+// that every tile index is static.  Returns true when a pivot was rejected (src/solver.jl:84-88).
+template <int AJ>
+__device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], unsigned& done, const int wid, const int lane,
+                                             double* mbuf, int* sh_pr, double* rd, double* UT) {
+  constexpr int UTLD = DENSE_UTLD;
+  if constexpr (AJ >= D3_CPN) {
+    return false;
+  } else {
+#pragma unroll 1
+    for (int wj = 0; wj < 16; ++wj) {
+      const int j = AJ * 16 + wj;
+      if (j >= NRED) break;
+      const int par = j & 1;
+      if (wid == wj) {   // this warp holds column j: pivot search and multipliers
+        unsigned key = 0;
+        double vbest = 0.0;   // value behind this lane's best key
+#pragma unroll
+        for (int b = 0; b < D3_RCH; ++b)
+          if (!((done >> b) & 1u)) {
+            const unsigned k = ((unsigned)__double2hiint(fabs(acc[b][AJ])) & 0xffffff00u) | (unsigned)(255 - (lane + 32 * b));
+            if (k > key) {
+              key = k;
+              vbest = acc[b][AJ];
+            }
+          }
+        const unsigned best = __reduce_max_sync(FULLMASK, key);
+        const int prr = 255 - (int)(best & 0xffu);
+        const double piv = __shfl_sync(FULLMASK, vbest, prr & 31);   // keys are unique per row: that lane's best is the pivot
+        const bool bad = best == 0 || !(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_);  // :84-88
+        const double rp = 1.0 / piv;
+#pragma unroll
+        for (int b = 0; b < D3_RCH; ++b) {
+          const int r = lane + 32 * b;
+          mbuf[par * 128 + r] = (!((done >> b) & 1u) && r != prr) ? -(acc[b][AJ] * rp) : 0.0;
+        }
+        if (lane == 0) {
+          sh_pr[par] = bad ? -1 : prr;
+          rd[j] = rp;
+        }
+      }
+      __syncthreads();
+      const int pr = sh_pr[par];
+      if (pr < 0) return true;
+      double m[D3_RCH];
+#pragma unroll
+      for (int b = 0; b < D3_RCH; ++b) m[b] = mbuf[par * 128 + lane + 32 * b];
+      const int src = pr & 31, pb = pr >> 5;
+      if (lane == src) done |= 1u << pb;
+      double u[D3_CPW];
+#pragma unroll
+      for (int a = AJ; a < D3_CPW; ++a) {
+        double v = d3_opaque(acc[0][a]);
+#pragma unroll
+        for (int b = 1; b < D3_RCH; ++b) v = (pb == b) ? d3_opaque(acc[b][a]) : v;
+        u[a] = __shfl_sync(FULLMASK, v, src);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int a = AJ; a < D3_CPW; ++a) {
+          const int c = wid + 16 * a;
+          if (c >= j && c <= NRED) UT[c * UTLD + j] = u[a];
+        }
+      }
+#pragma unroll
+      for (int a = AJ; a < D3_CPW; ++a)
+        if (a > AJ || wid > wj) {
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b) acc[b][a] = fma(m[b], u[a], acc[b][a]);
+        }
+    }
+    return d3_lu_blocks<AJ + 1>(acc, done, wid, lane, mbuf, sh_pr, rd, UT);
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const SolveParams p) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  const int wid = t >> 5, lane = t & 31;
+  double* x = smem + DENSE_OFF_X;
+  double* y = smem + DENSE_OFF_Y;
+  double* s = smem + DENSE_OFF_S;
+  double* g = smem + DENSE_OFF_G;
+  double* w = smem + DENSE_OFF_W;        // H rows, then w, then δy
+  double* dinv = smem + DENSE_OFF_DINV;  // D⁻¹, then δs
+  double* sol = smem + DENSE_OFF_SOL;    // right-hand side, then δx (new ordering)
+  double* jv = smem + DENSE_OFF_JV;      // computed Jacobian entries (none for these plans)
+  double* red = smem + DENSE_OFF_RED;    // 16 doubles of reduction scratch
+  double* rd = smem + DENSE_OFF_RD;      // reciprocal pivots
+  double* Hc = smem + DENSE_OFF_HC;      // H_x cached for the whole solve: NY rows × DENSE_HCS (column NRED stays 0)
+  double* xt = smem + DENSE_OFF_XT;      // x in the new ordering
+  double* gh0 = smem + DENSE_OFF_G0;     // G(0;θ), H(0;θ)
+  double* UT = smem + DENSE_OFF_UT;      // Uᵀ in pivot order: UT[c·UTLD + step]; row NRED = forward-substituted rhs
+  double* mbuf = smem + DENSE_OFF_MBUF;  // 2 × 128 multipliers of the current column (double-buffered by parity)
+  double* Gc = p.scratch + (size_t)blockIdx.x * SOLVE_SCRATCH;  // (G_x + tol·I)ᵀ, NRED columns × D3_GLD
+  constexpr int HCS = DENSE_HCS;
+  constexpr int UTLD = DENSE_UTLD;
+  __shared__ unsigned long long sh_q;
+  __shared__ int sh_pr[2];
+#if THETA_IN_SMEM
+  double* th = smem + DENSE_OFF_TH;
+#else
+  const double* th = p.theta;
+#endif
+  const double tol = p.tol;
+  const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+  unsigned pad_rows = 0;   // tile rows beyond NRED never take part in the factorisation
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b)
+    if (lane + 32 * b >= NRED) pad_rows |= 1u << b;
+
+  for (;;) {
+    __syncthreads();
+    if (t == 0) sh_q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+    __syncthreads();
+    unsigned long long inst = sh_q;
+    if (p.pass) {
+      if (inst >= n_deferred) break;
+      inst = (unsigned long long)p.deferred[inst];
+    } else if (inst >= (unsigned long long)p.B) {
+      break;
+    }
+#if THETA_IN_SMEM
+    for (int i = t; i < NT; i += DT) th[i] = p.theta[inst * NT + i];
+#else
+    th = p.theta + inst * NT;
+#endif
+    double eps = 1.0;                                        // :67
+    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // :68
+    int status = 0, outer = 1, steps = 0;                    // :69-70
+    if (p.pass) {
+      for (int i = t; i < NX; i += DT) x[i] = p.x_out[inst * NX + i];
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y_out[inst * NY + i];
+        s[i] = p.s_out[inst * NY + i];
+      }
+      eps = p.eps_out[inst];
+      kkt = p.kkt_out[inst];
+      outer = p.outer_out[inst];
+      steps = p.steps_out[inst];
+    } else {
+      for (int i = t; i < NX; i += DT) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+      for (int i = t; i < NY; i += DT) {
+        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      }
+    }
+    __syncthreads();
+    // ---- once per solve: cache H_x and G_x + tol·I (θ-only), evaluate the constant part of the residual ------------
+    for (int i = t; i < NY * HCS; i += DT) Hc[i] = 0.0;
+    for (int i = t; i < NRED * D3_GLD; i += DT) __stcg(Gc + i, 0.0);
+    if (t < 256) mcp_eval_const_par(t, x, y, th, gh0);
+    __syncthreads();
+    for (int k = wid; k < NY; k += DT / 32)
+      for (int e = H_PTR[k] + lane; e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+    for (int d = t; d < ND; d += DT) {
+      const int tp = D_TP[d], t1 = D_TP[d + 1] & 0x7fffffff;
+      double a0 = D_BASE[d] + ((tp < 0) ? tol : 0.0);
+      for (int q = tp & 0x7fffffff; q < t1; ++q) a0 += T_COEF[q] * opval(T_I[q].x, jv, th);
+      __stcg(Gc + D_CPOS[d] * D3_GLD + D_ROW[d], a0);
+    }
+    __syncthreads();
+    bool parked = false;
+    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
+        parked = true;
+        break;
+      }
+      int inner = 1;  // :72
+      status = 0;     // :73
+      while (kkt > eps && inner < p.max_inner) {  // :75
+        for (int c = t; c < NRED; c += DT) xt[c] = x[PERM[c]];
+        // ---- tile of the direct part G_x + tol·I ------------------------------------------------------------------
+        double acc[D3_RCH][D3_CPW];
+#pragma unroll
+        for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+          for (int a = 0; a < D3_CPW; ++a) {
+            const int r = lane + 32 * b, c = wid + 16 * a;
+            acc[b][a] = (r < NRED && c < NRED) ? __ldcg(Gc + c * D3_GLD + r) : 0.0;
+          }
+        __syncthreads();
+        // ---- F (:79) from the affine structure: H = H(0) + H_x x,  G = G(0) + G_x x + G_y y,  G_y = −H_xᵀ ----------
+        {
+          double* stage = UT;   // 16 × 128 partial row sums of (G_x + tol·I)·x, one slice per warp
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b) {
+            double sa = 0.0;
+#pragma unroll
+            for (int a = 0; a < D3_CPN; ++a) {
+              const int c = wid + 16 * a;
+              if (c < NRED) sa = fma(acc[b][a], xt[c], sa);
+            }
+            stage[wid * 128 + lane + 32 * b] = sa;
+          }
+        }
+        if (t < NY) {
+          double a0 = 0.0, a1 = 0.0;
+          const double* hr = Hc + t * HCS;
+#pragma unroll 4
+          for (int c = 0; c + 1 < NRED; c += 2) {
+            a0 = fma(hr[c], xt[c], a0);
+            a1 = fma(hr[c + 1], xt[c + 1], a1);
+          }
+          if (NRED & 1) a0 = fma(hr[NRED - 1], xt[NRED - 1], a0);
+          w[t] = gh0[NX + t] + a0 + a1;
+        }
+        __syncthreads();
+        if (t >= 128 && t < 128 + NRED) {  // G in the NEW row ordering (row i ↔ old row PERM[i])
+          const int i = t - 128;
+          double a1 = 0.0, a2 = 0.0, gx = 0.0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) gx += UT[q * 128 + i];
+#pragma unroll 4
+          for (int k = 0; k + 1 < NY; k += 2) {
+            a1 = fma(Hc[k * HCS + i], y[k], a1);
+            a2 = fma(Hc[(k + 1) * HCS + i], y[k + 1], a2);
+          }
+          if (NY & 1) a1 = fma(Hc[(NY - 1) * HCS + i], y[NY - 1], a1);
+          g[i] = (gh0[PERM[i]] - tol * xt[i] + gx) - (a1 + a2);
+        }
+        __syncthreads();
+        double fmax_ = 0.0;
+        for (int i = t; i < NX; i += DT) fmax_ = nanmax(fmax_, fabs(g[i]));
+        for (int k = t; k < NY; k += DT) {
+          const double f2 = w[k] - s[k];
+          const double f3 = s[k] * y[k] - eps;
+          const double yt = y[k] + tol;
+          const double di = 1.0 / (tol + s[k] / yt);
+          dinv[k] = di;
+          w[k] = di * (-f2 - f3 / yt);
+          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+        }
+        const double kkt_new = blk_nanmax(fmax_, red, t);  // :107 (also orders the writes above)
+        // ---- right-hand side: −G − G_y w = −G + H_xᵀ w, into column NRED of the tiles -----------------------------
+        if (t < NRED) {
+          double a0 = -g[t], a1 = 0.0;
+#pragma unroll 4
+          for (int k = 0; k + 1 < NY; k += 2) {
+            a0 = fma(Hc[k * HCS + t], w[k], a0);
+            a1 = fma(Hc[(k + 1) * HCS + t], w[k + 1], a1);
+          }
+          if (NY & 1) a0 = fma(Hc[(NY - 1) * HCS + t], w[NY - 1], a0);
+          sol[t] = a0 + a1;
+        }
+        // ---- Schur part: C −= G_y D⁻¹ H_x = + H_xᵀ D⁻¹ H_x, accumulated on the register tiles ----------------------
+#pragma unroll 2
+        for (int k = 0; k < NY; ++k) {
+          const double dk = dinv[k];
+          const double* hr = Hc + k * HCS;
+          double av[D3_RCH], bv[D3_CPW];
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b) av[b] = hr[min(lane + 32 * b, NRED)] * dk;
+#pragma unroll
+          for (int a = 0; a < D3_CPW; ++a) bv[a] = hr[min(wid + 16 * a, NRED)];
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+            for (int a = 0; a < D3_CPW; ++a) acc[b][a] = fma(av[b], bv[a], acc[b][a]);
+        }
+        __syncthreads();
+        if (wid == (NRED & 15)) {
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b) acc[b][NRED >> 4] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
+        }
+        // ---- LU with partial pivoting in registers; forward substitution rides in column NRED -----------------------
+        bool failed = false;
+        {
+          unsigned done = pad_rows;   // bit b: row lane+32b has been a pivot (same in every warp)
+          failed = d3_lu_blocks<0>(acc, done, wid, lane, mbuf, sh_pr, rd, UT);
+        }
+        __syncthreads();   // UT, rd complete (failed is CTA-uniform: every thread read the same key and pivot)
+        double a_s = 1.0, a_y = 1.0;
+        if (!failed) {
+          // ---- back substitution: column sweep over Uᵀ by one warp, right-hand side in registers ---------------------
+          if (wid == 0) {
+            double rhs[D3_RCH];
+#pragma unroll
+            for (int b = 0; b < D3_RCH; ++b) rhs[b] = (lane + 32 * b < NRED) ? UT[NRED * UTLD + lane + 32 * b] : 0.0;
+#pragma unroll
+            for (int bj = D3_RCH - 1; bj >= 0; --bj) {
+#pragma unroll 4
+              for (int lj = 31; lj >= 0; --lj) {
+                const int j = bj * 32 + lj;
+                if (j < NRED) {
+                  const double xj = __shfl_sync(FULLMASK, rhs[bj], lj) * rd[j];
+                  if (lane == lj) sol[j] = xj;
+                  const double* uc = UT + j * UTLD;
+#pragma unroll
+                  for (int b = 0; b <= bj; ++b) {
+                    const int i = lane + 32 * b;
+                    if (i < j) rhs[b] = fma(-uc[i], xj, rhs[b]);
+                  }
+                }
+              }
+            }
+          }
+          __syncthreads();
+          // ---- δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol) ---------------------------------------------------
+          if (t < NY) {
+            double a0 = 0.0, a1 = 0.0;
+            const double* hr = Hc + t * HCS;
+#pragma unroll 4
+            for (int c = 0; c + 1 < NRED; c += 2) {
+              a0 = fma(hr[c], sol[c], a0);
+              a1 = fma(hr[c + 1], sol[c + 1], a1);
+            }
+            if (NRED & 1) a0 = fma(hr[NRED - 1], sol[NRED - 1], a0);
+            const double dy = w[t] - dinv[t] * (a0 + a1);
+            const double f3 = s[t] * y[t] - eps;
+            w[t] = dy;
+            dinv[t] = -(f3 + s[t] * dy) / (y[t] + tol);
+          }
+          __syncthreads();
+          a_s = blk_ftb_linesearch(s, dinv, p.min_stepsize, t);  // :93
+          a_y = blk_ftb_linesearch(y, w, p.min_stepsize, t);     // :94
+          failed = (a_s != a_s) || (a_y != a_y);                 // :96-100
+        }
+        if (failed) {
+          status = 1;
+          break;
+        }
+        for (int c = t; c < NRED; c += DT) x[PERM[c]] += a_s * sol[c];  // :103
+        for (int k = t; k < NY; k += DT) {
+          s[k] += a_s * dinv[k];                                        // :104
+          y[k] += a_y * w[k];                                           // :105
+        }
+        __syncthreads();
+        kkt = kkt_new;  // :107
+        ++inner;        // :108
+        ++steps;
+      }
+      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
+      ++outer;                                                                                              // :114
+    }
+    if (!parked && outer == p.max_outer) status = 1;  // :117-119
+    for (int i = t; i < NX; i += DT) p.x_out[inst * NX + i] = x[i];
+    for (int i = t; i < NY; i += DT) {
+      p.y_out[inst * NY + i] = y[i];
+      p.s_out[inst * NY + i] = s[i];
+    }
+    if (t == 0) {
+      p.kkt_out[inst] = kkt;
+      p.eps_out[inst] = eps;
+      p.outer_out[inst] = outer;
+      p.status_out[inst] = status;
+      p.steps_out[inst] = steps;
+      if (parked) {
+        p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+      } else {
+        atomicAdd(p.counters + 1, (unsigned long long)steps);
+        if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+      }
+    }
+  }
+}
+#elif DENSE_KERNEL == 2
 extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const SolveParams p) {
   extern __shared__ double smem[];
   const int t = threadIdx.x;

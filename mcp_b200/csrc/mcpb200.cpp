@@ -304,7 +304,7 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   const long long ctas_needed = (p.B + P.ipc_solve - 1) / P.ipc_solve;
   const long long max_ctas = (long long)st->num_sms * (P.dense_kernel ? P.dense_ctas_per_sm : 1);
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
-  const unsigned block = P.dense_kernel ? 256u : (unsigned)(P.sub * P.ipc_solve);
+  const unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve);
   const size_t scratch_bytes = (size_t)st->num_sms * P.ipc_solve * P.scratch_doubles_solve * 8;
   if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * P.ipc_sens * P.scratch_doubles_sens * 8)))
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
@@ -482,7 +482,7 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->n_jac_constant = P.n_const_entries;
   info->n_assembly_dests = (int)P.d_row.size();
   info->n_assembly_terms = (int)P.t_coef.size();
-  info->threads_per_instance = P.dense_kernel ? 256 : P.sub;
+  info->threads_per_instance = P.dense_kernel ? P.dense_threads : P.sub;
   info->instances_per_cta = P.ipc_solve;
   info->ctas_per_sm = P.dense_kernel ? P.dense_ctas_per_sm : 1;
   info->smem_bytes_per_cta = (int)P.smem_solve;

@@ -813,7 +813,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   auto even = [](int64_t v) { return (v + 1) & ~int64_t(1); };
   int64_t off = 0;
   auto place = [&](const char* name, int64_t n) {
-    lay << "#define " << name << " " << off << "\n";
+    lay << "#undef " << name << "\n#define " << name << " " << off << "\n";
     off = even(off + n);
   };
   // The "window" region of shared memory is, over one Newton step: storage of G, term buffer of the
@@ -962,10 +962,45 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
         off = off_v1;
       }
     }
+    // v3: the matrix lives in register tiles of a 512-thread CTA (32 lanes × ≤4 row chunks, 16 warps × ≤7 columns);
+    // shared memory holds H_x, Uᵀ for the back substitution and the multipliers of the current column
+    bool want_v3 = P.dense_kernel == 2 && N + 1 <= 112 && ny <= 128;
+    if (const char* e = getenv("MCPB200_DENSE_KERNEL")) want_v3 = want_v3 && atoi(e) >= 3;
+    if (want_v3) {
+      const int64_t hcs = (N + 1) | 1, utld = N | 1;
+      const int64_t off_v2 = off;
+      off = 0;
+      place("DENSE_OFF_X", nx);
+      place("DENSE_OFF_Y", ny);
+      place("DENSE_OFF_S", ny);
+      place("DENSE_OFF_G", nx);
+      place("DENSE_OFF_W", ny);
+      place("DENSE_OFF_DINV", ny);
+      place("DENSE_OFF_SOL", N);
+      place("DENSE_OFF_JV", njv);
+      if (P.theta_in_smem) place("DENSE_OFF_TH", nt);
+      place("DENSE_OFF_RED", 16);
+      place("DENSE_OFF_RD", N);
+      place("DENSE_OFF_HC", (int64_t)ny * hcs);
+      place("DENSE_OFF_XT", N);
+      place("DENSE_OFF_G0", nx + ny);
+      place("DENSE_OFF_UT", std::max<int64_t>((int64_t)(N + 1) * utld, 16 * 128));
+      place("DENSE_OFF_MBUF", 2 * 128);
+      if (off * 8 <= kSmemBudget) {
+        P.dense_kernel = 3;
+        P.dense_threads = 512;
+        P.smem_solve = off * 8;
+        P.dense_ctas_per_sm = 1;
+        lay << "#define DENSE_UTLD " << utld << "\n";
+      } else {
+        off = off_v2;
+      }
+    }
   }
   P.smem_sens = (shared_table_doubles + sens_doubles * P.ipc_sens) * 8;
   const int64_t cval_doubles = even(nd) + 2;
   P.scratch_doubles_solve = cval_doubles + even((int64_t)N * uts) + 2;
+  if (P.dense_kernel == 3) P.scratch_doubles_solve = std::max<int64_t>(P.scratch_doubles_solve, (int64_t)N * 128);
   P.scratch_doubles_sens = P.scratch_doubles_solve;
   // algorithmic flops of one Newton step's KKT solve: banded LU with partial pivoting +
   // forward/back substitution, dense-in-band count; for dense plans ⅔n³ + 2n² plus the Schur product
@@ -1080,7 +1115,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   Emitter E(P);
   // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
   os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
-  if (P.dense_kernel != 2) {
+  if (P.dense_kernel < 2) {
     std::vector<std::pair<int32_t, std::string>> outs;
     for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], "g[" + std::to_string(i) + "]"});
     for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], "h[" + std::to_string(i) + "]"});
@@ -1091,7 +1126,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                                   "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
                   "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub);
   }
-  if (P.dense_kernel == 2) {
+  if (P.dense_kernel >= 2) {
     os << "// G(0;θ), H(0;θ): the constant part of the (affine in z) residual\n";
     ZeroTape Z = substitute_zero(P, P.gh_nodes);
     Emitter EZ(Z.tape);

@@ -70,6 +70,7 @@ struct Plan {
   int dense_schur = 0;
   int dense_kernel = 0;               // CTA-per-instance dense solve kernel (kernel_template.cuh, DENSE_KERNEL)
   int dense_ctas_per_sm = 1;
+  int dense_threads = 256;            // CTA size of the dense kernel (v3: 512)
   bool gy_is_mhxt = false, hx_zconst = false, affine = false;   // structure flags (dense kernel v2)
   std::vector<int32_t> gk_ptr, gk_row, gk_code;
   std::vector<double> gk_coef;
