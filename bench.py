@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.batch is None:   # lane-change: 2^18 (tail of never-converging instances amortised); QP: θ is 161 KB/instance
-        args.batch = {"lane_change": 1 << 18, "readme_qp": 1 << 20, "random_qp": 1 << 13}.get(args.workload, 1 << 16)
+        args.batch = {"lane_change": 1 << 18, "readme_qp": 1 << 20, "random_qp": 1 << 15}.get(args.workload, 1 << 16)
     if args.impl == "reference":
         return run_reference(args)
 

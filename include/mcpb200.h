@@ -127,6 +127,8 @@ typedef struct mcpb200_timing {
   int64_t launches;       /* kernels of this library launched by the last call */
   int64_t newton_steps;   /* total Newton steps taken by the last solve call (sum over instances) */
   int64_t solved;         /* instances with status 0 in the last solve call */
+  double pass0_ms;        /* part of kernel_ms spent in the first scheduling pass */
+  int64_t deferred;       /* instances parked by pass 0 and finished by pass 1 */
 } mcpb200_timing;
 
 typedef struct mcpb200_problem* mcpb200_handle;

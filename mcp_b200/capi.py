@@ -61,7 +61,8 @@ class Info(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("launches", C.c_int64), ("newton_steps", C.c_int64), ("solved", C.c_int64)]
+                ("launches", C.c_int64), ("newton_steps", C.c_int64), ("solved", C.c_int64),
+                ("pass0_ms", C.c_double), ("deferred", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

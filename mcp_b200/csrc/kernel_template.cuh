@@ -659,17 +659,59 @@ __device__ __forceinline__ double blk_ftb_linesearch(const double* RS v, const d
 #define D3_CPW ((NRED + 1 + 15) / 16)
 #define D3_CPN ((NRED + 15) / 16)
 #define D3_GLD 128
-// Keeps a select chain over tile registers from being rewritten as a dynamically indexed (local-memory) load.
-__device__ __forceinline__ double d3_opaque(double v) {
-  asm("" : "+d"(v));
-  return v;
+#ifndef D3_SCHUR_UNROLL
+#define D3_SCHUR_UNROLL 2
+#endif
+constexpr int kSchurUnroll = D3_SCHUR_UNROLL;
+#ifndef D3_LOOKAHEAD
+#define D3_LOOKAHEAD 0
+#endif
+
+// Pivot search for column j (tile column A of the calling warp, which holds the whole column) and publication of
+// the pivot row index, the reciprocal pivot and the multipliers of every row.  Partial pivoting with the same key
+// as the other kernels: truncated |value| first, lowest row index among ties.  Rows that have been pivots (and the
+// padding rows) are all-zero in the tiles — the update phase clears a row once it is stored in Uᵀ — so they need
+// no masking: their key is below that of any usable pivot and their multiplier is ∓0.  The reciprocal is taken
+// per lane on the lane's own best candidate, in the shadow of the warp-wide max.  This runs on ONE warp while the
+// other fifteen wait at the barrier, so it is written for the shortest dependent instruction chain.
+template <int A>
+__device__ __forceinline__ void d3_search(const double (&acc)[D3_RCH][D3_CPW], const int lane, const int j, double* mbuf,
+                                          int* sh_pr, double* rd) {
+  const int par = j & 1;
+  unsigned k[D3_RCH];
+  unsigned key = 0;
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b) {
+    k[b] = ((unsigned)__double2hiint(acc[b][A]) & 0x7fffff00u) | (unsigned)(255 - (lane + 32 * b));
+    key = max(key, k[b]);
+  }
+  double vbest = acc[0][A];
+#pragma unroll
+  for (int b = 1; b < D3_RCH; ++b) vbest = (k[b] == key) ? acc[b][A] : vbest;
+  const double rpl = 1.0 / vbest;
+  const unsigned best = __reduce_max_sync(FULLMASK, key);
+  const int prr = 255 - (int)(best & 0xffu);
+  const double piv = __shfl_sync(FULLMASK, vbest, prr & 31);   // keys are unique per row: that lane's best is the pivot
+  const double rp = __shfl_sync(FULLMASK, rpl, prr & 31);
+  const bool bad = !(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_);  // :84-88 (a finished or padding row can only win with 0)
+  double* mb = mbuf + par * 128 + lane;
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b) mb[32 * b] = -(acc[b][A] * rp);
+  if (lane == (prr & 31)) mbuf[par * 128 + prr] = 0.0;   // the pivot row itself (same thread as the store above)
+  if (lane == 0) {
+    sh_pr[par] = bad ? -1 : prr;
+    rd[j] = rp;
+  }
 }
 
 // 16 elimination steps (columns 16·AJ … 16·AJ+15) of the register-resident LU; AJ is a template parameter so
-// that every tile index is static.  Returns true when a pivot was rejected (src/solver.jl:84-88).
+// that every tile index is static.  With D3_LOOKAHEAD the owner of the NEXT column updates that column first and
+// runs its search while the other warps are still in their trailing updates (measured slower on B200: the owner's
+// extra work lengthens the step more than the overlap saves, so it is off by default).
+// Returns true when a pivot was rejected (src/solver.jl:84-88).
 template <int AJ>
-__device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], unsigned& done, const int wid, const int lane,
-                                             double* mbuf, int* sh_pr, double* rd, double* UT) {
+__device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], const int wid, const int lane, double* mbuf,
+                                             int* sh_pr, double* rd, double* UT) {
   constexpr int UTLD = DENSE_UTLD;
   if constexpr (AJ >= D3_CPN) {
     return false;
@@ -679,33 +721,9 @@ __device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], unsi
       const int j = AJ * 16 + wj;
       if (j >= NRED) break;
       const int par = j & 1;
-      if (wid == wj) {   // this warp holds column j: pivot search and multipliers
-        unsigned key = 0;
-        double vbest = 0.0;   // value behind this lane's best key
-#pragma unroll
-        for (int b = 0; b < D3_RCH; ++b)
-          if (!((done >> b) & 1u)) {
-            const unsigned k = ((unsigned)__double2hiint(fabs(acc[b][AJ])) & 0xffffff00u) | (unsigned)(255 - (lane + 32 * b));
-            if (k > key) {
-              key = k;
-              vbest = acc[b][AJ];
-            }
-          }
-        const unsigned best = __reduce_max_sync(FULLMASK, key);
-        const int prr = 255 - (int)(best & 0xffu);
-        const double piv = __shfl_sync(FULLMASK, vbest, prr & 31);   // keys are unique per row: that lane's best is the pivot
-        const bool bad = best == 0 || !(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_);  // :84-88
-        const double rp = 1.0 / piv;
-#pragma unroll
-        for (int b = 0; b < D3_RCH; ++b) {
-          const int r = lane + 32 * b;
-          mbuf[par * 128 + r] = (!((done >> b) & 1u) && r != prr) ? -(acc[b][AJ] * rp) : 0.0;
-        }
-        if (lane == 0) {
-          sh_pr[par] = bad ? -1 : prr;
-          rd[j] = rp;
-        }
-      }
+#if !D3_LOOKAHEAD
+      if (wid == wj) d3_search<AJ>(acc, lane, j, mbuf, sh_pr, rd);
+#endif
       __syncthreads();
       const int pr = sh_pr[par];
       if (pr < 0) return true;
@@ -713,30 +731,54 @@ __device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], unsi
 #pragma unroll
       for (int b = 0; b < D3_RCH; ++b) m[b] = mbuf[par * 128 + lane + 32 * b];
       const int src = pr & 31, pb = pr >> 5;
-      if (lane == src) done |= 1u << pb;
+      // Pivot row → U: lane src holds this warp's part of it in row chunk pb; it stores the entries straight into Uᵀ
+      // (transposed, pivot order — what the back substitution reads), clears them in the tile (a finished row must
+      // be all-zero, see d3_search) and the warp reads them back as broadcasts.
+      // pb is CTA-uniform, so the chunk is chosen by a branch around plain stores: no register selects.
+      double* ut = UT + wid * UTLD + j;
+      if (lane == src) {
+#define D3_PUT(B_)                                                                                          \
+  if (D3_RCH > B_ && pb == B_) {                                                                            \
+    _Pragma("unroll") for (int a = AJ; a < D3_CPW; ++a)                                                      \
+      if (16 * a + 15 <= NRED || wid + 16 * a <= NRED) ut[16 * a * UTLD] = acc[B_ < D3_RCH ? B_ : 0][a];     \
+    _Pragma("unroll") for (int a = AJ; a < D3_CPW; ++a) acc[B_ < D3_RCH ? B_ : 0][a] = 0.0;                  \
+  }
+        D3_PUT(0) else D3_PUT(1) else D3_PUT(2) else D3_PUT(3)
+#undef D3_PUT
+      }
+      __syncwarp();
       double u[D3_CPW];
 #pragma unroll
-      for (int a = AJ; a < D3_CPW; ++a) {
-        double v = d3_opaque(acc[0][a]);
+      for (int a = AJ; a < D3_CPW; ++a) u[a] = (16 * a + 15 <= NRED || wid + 16 * a <= NRED) ? ut[16 * a * UTLD] : 0.0;
+      // look-ahead: column j+1
+      int la = -1;   // tile column already updated by the look-ahead
+#if D3_LOOKAHEAD
+      if (j + 1 < NRED) {
+        if (wj < 15) {
+          if (wid == wj + 1) {
 #pragma unroll
-        for (int b = 1; b < D3_RCH; ++b) v = (pb == b) ? d3_opaque(acc[b][a]) : v;
-        u[a] = __shfl_sync(FULLMASK, v, src);
-      }
-      if (lane == 0) {
+            for (int b = 0; b < D3_RCH; ++b) acc[b][AJ] = fma(m[b], u[AJ], acc[b][AJ]);
+            d3_search<AJ>(acc, lane, j + 1, mbuf, sh_pr, rd);
+            la = AJ;
+          }
+        } else if constexpr (AJ + 1 < D3_CPN) {
+          if (wid == 0) {
 #pragma unroll
-        for (int a = AJ; a < D3_CPW; ++a) {
-          const int c = wid + 16 * a;
-          if (c >= j && c <= NRED) UT[c * UTLD + j] = u[a];
+            for (int b = 0; b < D3_RCH; ++b) acc[b][AJ + 1] = fma(m[b], u[AJ + 1], acc[b][AJ + 1]);
+            d3_search<AJ + 1>(acc, lane, j + 1, mbuf, sh_pr, rd);
+            la = AJ + 1;
+          }
         }
       }
+#endif
 #pragma unroll
       for (int a = AJ; a < D3_CPW; ++a)
-        if (a > AJ || wid > wj) {
+        if ((a > AJ || wid > wj) && a != la) {
 #pragma unroll
           for (int b = 0; b < D3_RCH; ++b) acc[b][a] = fma(m[b], u[a], acc[b][a]);
         }
     }
-    return d3_lu_blocks<AJ + 1>(acc, done, wid, lane, mbuf, sh_pr, rd, UT);
+    return d3_lu_blocks<AJ + 1>(acc, wid, lane, mbuf, sh_pr, rd, UT);
   }
 }
 
@@ -771,10 +813,6 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
 #endif
   const double tol = p.tol;
   const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
-  unsigned pad_rows = 0;   // tile rows beyond NRED never take part in the factorisation
-#pragma unroll
-  for (int b = 0; b < D3_RCH; ++b)
-    if (lane + 32 * b >= NRED) pad_rows |= 1u << b;
 
   for (;;) {
     __syncthreads();
@@ -911,7 +949,7 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
           sol[t] = a0 + a1;
         }
         // ---- Schur part: C −= G_y D⁻¹ H_x = + H_xᵀ D⁻¹ H_x, accumulated on the register tiles ----------------------
-#pragma unroll 2
+#pragma unroll kSchurUnroll
         for (int k = 0; k < NY; ++k) {
           const double dk = dinv[k];
           const double* hr = Hc + k * HCS;
@@ -933,8 +971,10 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
         // ---- LU with partial pivoting in registers; forward substitution rides in column NRED -----------------------
         bool failed = false;
         {
-          unsigned done = pad_rows;   // bit b: row lane+32b has been a pivot (same in every warp)
-          failed = d3_lu_blocks<0>(acc, done, wid, lane, mbuf, sh_pr, rd, UT);
+#if D3_LOOKAHEAD
+          if (wid == 0) d3_search<0>(acc, lane, 0, mbuf, sh_pr, rd);
+#endif
+          failed = d3_lu_blocks<0>(acc, wid, lane, mbuf, sh_pr, rd, UT);
         }
         __syncthreads();   // UT, rd complete (failed is CTA-uniform: every thread read the same key and pivot)
         double a_s = 1.0, a_y = 1.0;

@@ -1018,6 +1018,14 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   // ---- source ----------------------------------------------------------------------------------------------
   std::ostringstream os;
   os << "// generated by libmcpb200 (plan.cpp) — do not edit\n";
+  if (const char* e = getenv("MCPB200_DEFS")) {   // kernel tuning experiments: "NAME=VALUE,NAME=VALUE"
+    std::string d(e), item;
+    std::istringstream is(d);
+    while (std::getline(is, item, ',')) {
+      const size_t eq = item.find('=');
+      if (eq != std::string::npos) os << "#define " << item.substr(0, eq) << " " << item.substr(eq + 1) << "\n";
+    }
+  }
   os << "#define NX " << nx << "\n#define NY " << ny << "\n#define NT " << nt << "\n#define NRED " << N << "\n";
   os << "#define KL " << P.kl << "\n#define KU " << P.ku << "\n#define WC " << P.WC << "\n#define WR " << P.R << "\n";
   os << "#define WS1 " << P.WS1 << "\n#define WSS " << P.WSS << "\n#define NRHS_SENS " << P.nrhs_sens << "\n";

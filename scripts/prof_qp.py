@@ -7,4 +7,5 @@ qp = problems.random_qp(100, 100)
 Θ = problems.random_qp_thetas(B, seed=1)
 for rep in range(2):
     sol = solve(InteriorPoint(), qp, Θ, tol=1e-6)
-print("kernel ms", _handle(qp).timing()["kernel_ms"], "solved", int((sol.status == 0).sum()), "steps", int(sol.newton_steps.sum()))
+tm = _handle(qp).timing()
+print("kernel ms", tm["kernel_ms"], "pass0 ms", tm["pass0_ms"], "deferred", tm["deferred"], "solved", int((sol.status == 0).sum()), "steps", int(sol.newton_steps.sum()))

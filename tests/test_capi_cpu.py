@@ -150,11 +150,15 @@ def test_plan_variants_are_selected_and_compile(monkeypatch, tmp_path):
     # tiny QP: two instances per warp
     m = _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())
     assert (m["SUB"], m["DENSE_KERNEL"]) == ("16", "0")
-    # dense QP with G_y = −H_xᵀ and an affine residual: CTA-per-instance kernel with H_x cached per solve
+    # dense QP with G_y = −H_xᵀ and an affine residual: CTA-per-instance kernel, matrix in register tiles (v3)
     h = capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY)
     m = _macros(h.source())
-    assert (m["DENSE_KERNEL"], m["DENSE_SCHUR"]) == ("2", "1") and h.info()["threads_per_instance"] == 256
+    assert (m["DENSE_KERNEL"], m["DENSE_SCHUR"]) == ("3", "1") and h.info()["threads_per_instance"] == 512
     assert "mcp_eval_const_par" in h.source() and "mcp_eval_newton_p0" not in h.source()
+    # v2 keeps the matrix in shared memory (256 threads), H_x cached per solve
+    monkeypatch.setenv("MCPB200_DENSE_KERNEL", "2")
+    h = capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["DENSE_KERNEL"] == "2" and h.info()["threads_per_instance"] == 256
     # the same problem with the v2 structure requirements switched off falls back to v1, then to the window kernel
     monkeypatch.setenv("MCPB200_DENSE_KERNEL", "1")
     assert _macros(capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY).source())["DENSE_KERNEL"] == "1"

@@ -233,6 +233,28 @@ def test_random_qp_100x100():
         assert rel_err(warm.x[:, b], refw.x[:, b]) <= RTOL
 
 
+@pytest.mark.parametrize("n,m,threads", [(37, 53, 512), (64, 40, 512), (96, 100, 512), (104, 96, 512), (111, 128, 256)])
+def test_dense_kernel_shapes(n, m, threads):
+    """The register-tiled dense kernel pads rows to 32-lane chunks and columns to 16-warp groups; these shapes hit
+    the partial chunk, the exact-multiple and the largest cases (the right-hand side is column n); the last one does
+    not fit the register-tiled kernel's shared memory and must fall back to the shared-memory dense kernel."""
+    mcp = problems.random_qp(n, m)
+    from mcp_b200.solver import _handle
+    info = _handle(mcp).info()
+    assert info["threads_per_instance"] == threads, info
+    Θ = problems.random_qp_thetas(6, seed=n + m, num_primals=n, num_inequalities=m, sparsity_rate=0.8)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    from oracle import c_oracle as CO
+    ref = CO.solve_batch(mcp.ir, Θ, tol=1e-6)
+    np.testing.assert_array_equal(sol.status, ref.status)
+    ok = sol.status == 0
+    assert ok.sum() >= 2
+    assert np.all(np.abs(sol.newton_steps[ok] - ref.newton_steps[ok]) <= 1)
+    for b in np.nonzero(ok)[0]:
+        assert rel_err(sol.x[:, b], ref.x[:, b]) <= RTOL and rel_err(sol.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------------------
 def test_empty_and_single_batches(readme_mcp):
     empty = solve(InteriorPoint(), readme_mcp, np.zeros((2, 0)))
