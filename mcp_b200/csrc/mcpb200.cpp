@@ -221,10 +221,93 @@ void write_file(const std::string& path, const char* data, size_t n) {
   rename(tmp.c_str(), path.c_str());
 }
 
+// ---- nvJitLink, bound at run time ------------------------------------------------------------------------------
+// The library is NOT linked: a host process that imported torch has already mapped torch's own libnvJitLink.so.12
+// (an older minor version without the symbol versions this toolkit's header would bind).  The toolkit's copy is
+// opened by absolute path into its own namespace and its entry points are looked up by name.
+struct JitLink {
+  using Handle = void*;
+  int (*Create)(Handle*, uint32_t, const char**) = nullptr;
+  int (*Destroy)(Handle*) = nullptr;
+  int (*AddData)(Handle, int, const void*, size_t, const char*) = nullptr;
+  int (*Complete)(Handle) = nullptr;
+  int (*GetLinkedCubinSize)(Handle, size_t*) = nullptr;
+  int (*GetLinkedCubin)(Handle, void*) = nullptr;
+  int (*GetErrorLogSize)(Handle, size_t*) = nullptr;
+  int (*GetErrorLog)(Handle, char*) = nullptr;
+  bool ok = false;
+  std::string err;
+};
+constexpr int kJitLinkInputCubin = 1;   // NVJITLINK_INPUT_CUBIN
+
+JitLink& jitlink() {
+  static JitLink j;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* lib = nullptr;
+    std::vector<std::string> names;
+    if (const char* e = getenv("CUDA_HOME")) names.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
+    names.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
+    names.push_back("libnvJitLink.so.12");
+    for (const std::string& n : names)
+      if ((lib = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL))) break;
+    if (!lib) {
+      j.err = "libnvJitLink.so.12 not found (needed to link the separately compiled evaluation units)";
+      return;
+    }
+    auto sym = [&](const char* base) -> void* {
+      for (int minor = 9; minor >= 0; --minor) {
+        const std::string n = std::string("__") + base + "_12_" + std::to_string(minor);
+        if (void* f = dlsym(lib, n.c_str())) return f;
+      }
+      return dlsym(lib, base);
+    };
+    j.Create = (decltype(j.Create))sym("nvJitLinkCreate");
+    j.Destroy = (decltype(j.Destroy))sym("nvJitLinkDestroy");
+    j.AddData = (decltype(j.AddData))sym("nvJitLinkAddData");
+    j.Complete = (decltype(j.Complete))sym("nvJitLinkComplete");
+    j.GetLinkedCubinSize = (decltype(j.GetLinkedCubinSize))sym("nvJitLinkGetLinkedCubinSize");
+    j.GetLinkedCubin = (decltype(j.GetLinkedCubin))sym("nvJitLinkGetLinkedCubin");
+    j.GetErrorLogSize = (decltype(j.GetErrorLogSize))sym("nvJitLinkGetErrorLogSize");
+    j.GetErrorLog = (decltype(j.GetErrorLog))sym("nvJitLinkGetErrorLog");
+    j.ok = j.Create && j.Destroy && j.AddData && j.Complete && j.GetLinkedCubinSize && j.GetLinkedCubin && j.GetErrorLogSize && j.GetErrorLog;
+    if (!j.ok) j.err = "libnvJitLink.so.12 lacks an expected entry point";
+  });
+  return j;
+}
+
+// One NVRTC compilation to a cubin (relocatable when `rdc`).  Returns an empty string on success, else the log.
+std::string nvrtc_to_cubin(const std::string& src, const std::string& name, bool rdc, bool lineinfo, std::vector<char>& cubin) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) return "nvrtcCreateProgram failed";
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
+  if (lineinfo) opts.push_back("-lineinfo");
+  if (rdc) opts.push_back("--relocatable-device-code=true");
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    if (log.size() > 4000) log.resize(4000);
+    return std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log;
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  cubin.resize(n);
+  nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return n ? std::string() : std::string("NVRTC produced an empty cubin");
+}
+
 int compile_source(mcpb200_problem* h, uint32_t flags) {
   const std::string& src = h->plan.source;
+  const std::vector<std::string>& units = h->plan.units;
+  unsigned long long hsh = fnv1a(src + "|sm_100a|v" + std::to_string(MCPB200_VERSION));
+  for (const std::string& u : units) hsh = hsh * 1099511628211ULL ^ fnv1a(u);
   char key[32];
-  snprintf(key, sizeof key, "%016llx", (unsigned long long)fnv1a(src + "|sm_100a|v" + std::to_string(MCPB200_VERSION)));
+  snprintf(key, sizeof key, "%016llx", hsh);
   const std::string dir = cache_dir();
   const std::string cu_path = dir + "/mcp_" + key + ".cu";
   const std::string bin_path = dir + "/mcp_" + key + ".cubin";
@@ -237,26 +320,58 @@ int compile_source(mcpb200_problem* h, uint32_t flags) {
     mkdir(dir.c_str(), 0755);
     write_file(cu_path, src.data(), src.size());  // lets ncu --import-source map SASS to the generated source
   }
-  nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, src.c_str(), cu_path.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
-    return set_err(h, MCPB200_ERR_COMPILE, "nvrtcCreateProgram failed");
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-default-device"};
-  nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
-  if (r != NVRTC_SUCCESS) {
+  if (units.empty()) {
+    const std::string err = nvrtc_to_cubin(src, cu_path, false, true, h->cubin);
+    if (!err.empty()) return set_err(h, MCPB200_ERR_COMPILE, err);
+  } else {
+    // Big problems: the evaluation parts are separate relocatable units, compiled concurrently (NVRTC is
+    // thread-safe across programs) and linked with the kernels by nvJitLink.
+    const size_t nu = units.size();
+    std::vector<std::vector<char>> objs(nu + 1);
+    std::vector<std::string> errs(nu + 1);
+    std::atomic<size_t> next{0};
+    unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)(nu + 1)));
+    if (const char* e = getenv("MCPB200_COMPILE_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+    auto worker = [&] {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i > nu) break;
+        errs[i] = (i == 0) ? nvrtc_to_cubin(src, cu_path, true, true, objs[0])
+                           : nvrtc_to_cubin(units[i - 1], cu_path + ".unit" + std::to_string(i - 1), true, false, objs[i]);  // (sources of the units are not kept: no line info)
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    for (size_t i = 0; i <= nu; ++i)
+      if (!errs[i].empty()) return set_err(h, MCPB200_ERR_COMPILE, "unit " + std::to_string(i) + ": " + errs[i]);
+    JitLink& J = jitlink();
+    if (!J.ok) return set_err(h, MCPB200_ERR_COMPILE, J.err);
+    JitLink::Handle L = nullptr;
+    const char* lopts[] = {"-arch=sm_100a", "-lineinfo"};
+    if (J.Create(&L, 2, lopts) != 0) return set_err(h, MCPB200_ERR_COMPILE, "nvJitLinkCreate failed");
+    auto link_fail = [&](const char* what) {
+      size_t n = 0;
+      std::string log;
+      if (J.GetErrorLogSize(L, &n) == 0 && n) {
+        log.resize(n);
+        J.GetErrorLog(L, &log[0]);
+      }
+      J.Destroy(&L);
+      if (log.size() > 4000) log.resize(4000);
+      return set_err(h, MCPB200_ERR_COMPILE, std::string("nvJitLink: ") + what + "\n" + log);
+    };
+    for (size_t i = 0; i <= nu; ++i)
+      if (J.AddData(L, kJitLinkInputCubin, objs[i].data(), objs[i].size(), ("unit" + std::to_string(i)).c_str()) != 0)
+        return link_fail("add failed");
+    if (J.Complete(L) != 0) return link_fail("link failed");
     size_t n = 0;
-    nvrtcGetProgramLogSize(prog, &n);
-    std::string log(n, '\0');
-    if (n) nvrtcGetProgramLog(prog, &log[0]);
-    nvrtcDestroyProgram(&prog);
-    if (log.size() > 4000) log.resize(4000);
-    return set_err(h, MCPB200_ERR_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+    if (J.GetLinkedCubinSize(L, &n) != 0 || n == 0) return link_fail("empty result");
+    h->cubin.resize(n);
+    J.GetLinkedCubin(L, h->cubin.data());
+    J.Destroy(&L);
   }
-  size_t n = 0;
-  nvrtcGetCUBINSize(prog, &n);
-  h->cubin.resize(n);
-  nvrtcGetCUBIN(prog, h->cubin.data());
-  nvrtcDestroyProgram(&prog);
-  if (n == 0) return set_err(h, MCPB200_ERR_COMPILE, "NVRTC produced an empty cubin");
   if (use_cache) write_file(bin_path, h->cubin.data(), h->cubin.size());
   return MCPB200_OK;
 }

@@ -349,9 +349,13 @@ struct Emitter {
     return key;
   }
 
+  // `units` (optional): when the evaluation is large, the part functions go into separately compiled translation
+  // units of ~kUnitParts parts each (relocatable device code, linked with nvJitLink by the caller) and `os` only
+  // gets their declarations: one translation unit of 30 MB takes NVRTC tens of GB and tens of minutes, the units
+  // compile in parallel in a few hundred MB each.
   void partitioned(std::ostringstream& os, const std::string& name, const std::string& params,
                    const std::string& args, std::vector<std::pair<int32_t, std::string>> outs,
-                   int max_parts) const {
+                   int max_parts, std::vector<std::string>* units = nullptr, const std::string& unit_prelude = "") const {
     {
       const std::vector<int32_t> key = locality_keys();
       std::stable_sort(outs.begin(), outs.end(), [&](const auto& a, const auto& b) { return key[a.first] < key[b.first]; });
@@ -364,6 +368,7 @@ struct Emitter {
     // at most one part per lane while parts stay small; beyond ~kPartNodes tape nodes per part ptxas time explodes
     // (superlinear in function size), so big problems get more parts and every lane loops over several
     constexpr long kPartNodes = 600;
+    constexpr int kSplitParts = 24, kUnitParts = 6;
     const long by_lanes = std::min<long>(max_parts, total / 24 + 1);
     const int K = (int)std::max<long>(1, std::min<long>((long)outs.size(), std::max<long>(by_lanes, (total + kPartNodes - 1) / kPartNodes)));
     std::vector<size_t> begin(K + 1, outs.size());
@@ -376,12 +381,27 @@ struct Emitter {
         if (acc * K >= total * part) begin[part++] = i + 1;
       }
     }
+    bool split = units && K >= kSplitParts;
+    if (const char* e = getenv("MCPB200_SPLIT_COMPILE")) split = units && atoi(e) != 0;
+    std::ostringstream unit;
+    int in_unit = 0;
     for (int k = 0; k < K; ++k) {
-      os << "__device__ __noinline__ void " << name << "_p" << k << "(" << params << ") {\n";
+      std::ostringstream& dst = split ? unit : os;
+      if (split && in_unit == 0) unit << unit_prelude;
+      dst << "__device__ __noinline__ void " << name << "_p" << k << "(" << params << ") {\n";
       std::vector<int32_t> sub(roots.begin() + begin[k], roots.begin() + begin[k + 1]);
-      body(os, sub);
-      for (size_t i = begin[k]; i < begin[k + 1]; ++i) os << "  " << outs[i].second << " = " << operand(outs[i].first) << ";\n";
-      os << "}\n";
+      body(dst, sub);
+      for (size_t i = begin[k]; i < begin[k + 1]; ++i) dst << "  " << outs[i].second << " = " << operand(outs[i].first) << ";\n";
+      dst << "}\n";
+      if (split) {
+        os << "extern __device__ void " << name << "_p" << k << "(" << params << ");\n";
+        if (++in_unit == kUnitParts || k == K - 1) {
+          units->push_back(unit.str());
+          unit.str("");
+          unit.clear();
+          in_unit = 0;
+        }
+      }
     }
     os << "__device__ __forceinline__ void " << name << "_par(int lane, " << params << ") {\n";
     os << "#pragma unroll 1\n  for (int part = lane; part < " << K << "; part += " << max_parts << ")\n  switch (part) {\n";
@@ -1122,10 +1142,14 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     emit_table(os, "int", "Q_CODE", P.q_code);
     emit_table(os, "double", "Q_COEF", P.q_coef, true);
   }
-  os << "__device__ __forceinline__ double mcp_powi(double a, int n) {\n"
-        "  double r = 1.0; bool neg = n < 0; if (neg) n = -n;\n"
-        "  while (n) { if (n & 1) r *= a; a *= a; n >>= 1; }\n"
-        "  return neg ? 1.0 / r : r;\n}\n";
+  const std::string powi_src =
+      "__device__ __forceinline__ double mcp_powi(double a, int n) {\n"
+      "  double r = 1.0; bool neg = n < 0; if (neg) n = -n;\n"
+      "  while (n) { if (n & 1) r *= a; a *= a; n >>= 1; }\n"
+      "  return neg ? 1.0 / r : r;\n}\n";
+  os << powi_src;
+  const std::string unit_prelude = "// generated by libmcpb200 (plan.cpp): evaluation parts, compiled separately — do not edit\n" + powi_src;
+  P.units.clear();
   Emitter E(P);
   // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
   os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
@@ -1138,7 +1162,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                   P.large_state ? "const double* x, const double* y, const double* th, double* g, double* h, double* jv"
                                 : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                                   "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
-                  "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub);
+                  "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub, &P.units, unit_prelude);
   }
   if (P.dense_kernel >= 2) {
     os << "// G(0;θ), H(0;θ): the constant part of the (affine in z) residual\n";
@@ -1163,7 +1187,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                     P.large_state ? "const double* x, const double* y, const double* th, double* jv, double* jtv"
                                   : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                                     "double* __restrict__ jv, double* __restrict__ jtv",
-                    "x, y, th, jv, jtv", outs, P.sub);
+                    "x, y, th, jv, jtv", outs, P.sub, &P.units, unit_prelude);
     }
   }
   os << kernel_template;

@@ -87,7 +87,8 @@ struct Plan {
   int64_t scratch_doubles_solve = 0, scratch_doubles_sens = 0;  // per warp, global memory
   double flops_band = 0.0;
 
-  std::string source;                 // generated CUDA translation unit
+  std::string source;                 // generated CUDA translation unit (tables, dispatchers, kernels)
+  std::vector<std::string> units;     // big problems: the generated evaluation parts, split into separately compiled units
   std::string error;
 };
 

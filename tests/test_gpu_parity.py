@@ -372,6 +372,29 @@ def test_masked_game_n4():
     assert g.shape == (40, 16) and np.all(np.isfinite(g[:, sol.status == 0]))
 
 
+def test_masked_game_n10():
+    """The application's largest configuration (SURVEY.md §8 cfg4, N = 10): nx = 3000, ny = 3630, nθ = 160, 200 k tape
+    nodes.  The evaluation is compiled as separately linked units, the state lives in the global block (large-state
+    mode) and the window (57 × 113) in shared memory.  Four scenarios against the C oracle."""
+    from oracle import c_oracle as CO
+    game = problems.masked_game(10, 30)
+    mcp = game.mcp
+    assert (mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension) == (3000, 3630, 160)
+    Θ = problems.masked_game_thetas(4, 10, seed=1)
+    x0 = problems.masked_game_x0(Θ, 10, 30)
+    sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
+    ref = CO.solve_batch(mcp.ir, Θ, x0=x0, tol=1e-4)
+    np.testing.assert_array_equal(sol.status, ref.status)
+    assert (sol.status == 0).sum() >= 3
+    for b in np.nonzero(ref.status == 0)[0]:
+        assert abs(int(sol.newton_steps[b]) - int(ref.newton_steps[b])) <= 1
+        assert rel_err(sol.x[:, b], ref.x[:, b]) <= RTOL and rel_err(sol.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
+    from mcp_b200 import solve_pullback
+    g = solve_pullback(mcp, sol, Θ, 2 * sol.x, None, None)
+    assert g.shape == (160, 4) and np.all(np.isfinite(g[:, sol.status == 0]))
+
+
 def test_lane_change_parity_statistics(lane_game):
     """1 024 random lane-change instances against the C oracle: how often does the GPU follow the oracle's
     trajectory to the bar (same status, Newton steps within ±1, x/y/s within 1e-6 relative)?  Decisions taken
