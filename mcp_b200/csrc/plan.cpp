@@ -368,7 +368,7 @@ struct Emitter {
     // at most one part per lane while parts stay small; beyond ~kPartNodes tape nodes per part ptxas time explodes
     // (superlinear in function size), so big problems get more parts and every lane loops over several
     constexpr long kPartNodes = 600;
-    constexpr int kSplitParts = 24, kUnitParts = 6;
+    constexpr int kSplitParts = 96, kUnitParts = 6;   // (cross-unit calls cost: small problems stay in one unit)
     const long by_lanes = std::min<long>(max_parts, total / 24 + 1);
     const int K = (int)std::max<long>(1, std::min<long>((long)outs.size(), std::max<long>(by_lanes, (total + kPartNodes - 1) / kPartNodes)));
     std::vector<size_t> begin(K + 1, outs.size());
@@ -407,6 +407,194 @@ struct Emitter {
     os << "#pragma unroll 1\n  for (int part = lane; part < " << K << "; part += " << max_parts << ")\n  switch (part) {\n";
     for (int k = 0; k < K; ++k) os << "    case " << k << ": " << name << "_p" << k << "(" << args << "); break;\n";
     os << "    default: break;\n  }\n}\n";
+  }
+
+  // ---- shape-grouped evaluation ---------------------------------------------------------------------------------
+  // Trajectory games repeat a handful of expression shapes over stages and player pairs (the masked game at N = 10
+  // has 25 k outputs and 200 k tape nodes, but few distinct per-output expression DAGs once the leaf indices are
+  // abstracted).  Outputs whose DAG has the same shape are evaluated by ONE function, lanes in lockstep over the
+  // instances of the shape, with the leaf indices / constants that differ read from tables: no lane divergence
+  // and code size independent of the number of stages.  (The lane-partitioned functions below run 32 different
+  // code paths per warp, i.e. serialised, and their code grows with the problem: 109 MB of SASS for that game.)
+  struct OutT {
+    int32_t node;
+    int arr;       // index into the target array names
+    int32_t idx;
+  };
+  struct ShapeOp {
+    int op, a, b;  // operand refs: >= 0 interior (local id), < 0 leaf (-1 - local leaf id); POWI: b = exponent
+  };
+  struct Shape {
+    int arr = 0;
+    int root = 0;                        // operand ref of the output value
+    std::vector<int> leaf_kind;          // MCPB200_OP_{CONST,X,Y,THETA} per local leaf
+    std::vector<ShapeOp> ops;
+    std::vector<std::vector<int64_t>> leaf_val;   // [instance][leaf]: index, or (for constants) index into P.consts
+    std::vector<int32_t> out_idx;
+  };
+  static constexpr int kMaxShapeNodes = 96;
+  static constexpr int kMinShapeInstances = 6;
+
+  // local DAG of one output; false when it has more than kMaxShapeNodes interior nodes
+  bool output_shape(int root, std::string& sig, Shape& sh, std::vector<int64_t>& leaves) const {
+    std::map<int, int> interior, leaf;
+    sh.ops.clear();
+    sh.leaf_kind.clear();
+    leaves.clear();
+    auto ref = [&](int n) -> int {
+      if (is_leaf(P.op[n])) {
+        auto it = leaf.find(n);
+        if (it == leaf.end()) {
+          it = leaf.emplace(n, (int)leaf.size()).first;
+          sh.leaf_kind.push_back(P.op[n]);
+          leaves.push_back(P.a[n]);
+        }
+        return -1 - it->second;
+      }
+      return interior.at(n);
+    };
+    std::vector<std::pair<int, int>> stack;
+    if (!is_leaf(P.op[root])) stack.push_back({root, 0});
+    while (!stack.empty()) {
+      auto& top = stack.back();
+      const int n = top.first;
+      const int nops = is_binary(P.op[n]) ? 2 : 1;
+      if (top.second < nops) {
+        const int child = (top.second == 0) ? P.a[n] : P.b[n];
+        ++top.second;
+        if (!is_leaf(P.op[child]) && !interior.count(child)) stack.push_back({child, 0});
+        continue;
+      }
+      stack.pop_back();
+      if (interior.count(n)) continue;
+      if ((int)sh.ops.size() >= kMaxShapeNodes) return false;
+      ShapeOp o{P.op[n], ref(P.a[n]), is_binary(P.op[n]) ? ref(P.b[n]) : (P.op[n] == MCPB200_OP_POWI ? P.b[n] : 0)};
+      interior.emplace(n, (int)sh.ops.size());
+      sh.ops.push_back(o);
+    }
+    sh.root = ref(root);
+    std::ostringstream g;
+    for (const ShapeOp& o : sh.ops) g << o.op << ":" << o.a << ":" << o.b << ";";
+    g << "|";
+    for (int k : sh.leaf_kind) g << k << ",";
+    g << "|" << sh.root;
+    sig = g.str();
+    return true;
+  }
+
+  // Emits `name`_par(lane, …): shape-grouped functions for the outputs that repeat, the lane-partitioned functions
+  // (`partitioned`) for the rest.
+  void evaluation(std::ostringstream& os, const std::string& name, const std::string& params, const std::string& args,
+                  const std::vector<OutT>& outs, const std::vector<std::string>& arrays, int max_parts,
+                  std::vector<std::string>* units, const std::string& unit_prelude, bool use_shapes) const {
+    std::vector<Shape> shapes;
+    std::map<std::string, int> by_sig;
+    std::vector<int> shape_of(outs.size(), -1);
+    if (use_shapes) {
+      std::string sig;
+      Shape tmp;
+      std::vector<int64_t> leaves;
+      for (size_t i = 0; i < outs.size(); ++i) {
+        if (!output_shape(outs[i].node, sig, tmp, leaves)) continue;
+        sig += "|" + std::to_string(outs[i].arr);
+        auto it = by_sig.find(sig);
+        if (it == by_sig.end()) {
+          it = by_sig.emplace(sig, (int)shapes.size()).first;
+          shapes.push_back(tmp);
+          shapes.back().arr = outs[i].arr;
+        }
+        Shape& sh = shapes[it->second];
+        sh.leaf_val.push_back(leaves);
+        sh.out_idx.push_back(outs[i].idx);
+        shape_of[i] = it->second;
+      }
+    }
+    std::vector<std::pair<int32_t, std::string>> rest;
+    for (size_t i = 0; i < outs.size(); ++i) {
+      const int sidx = shape_of[i];
+      if (sidx < 0 || (int)shapes[sidx].out_idx.size() < kMinShapeInstances)
+        rest.push_back({outs[i].node, arrays[outs[i].arr] + "[" + std::to_string(outs[i].idx) + "]"});
+    }
+    // small sets of shape functions are inlined into the kernel (lane-change: 2 % faster than calls), big ones stay
+    // separate functions to keep the kernel's code size and ptxas time bounded
+    size_t shape_ops = 0;
+    for (const Shape& sh : shapes)
+      if ((int)sh.out_idx.size() >= kMinShapeInstances) shape_ops += sh.ops.size() + sh.leaf_kind.size();
+    bool inline_shapes = shape_ops <= 3000;
+    if (const char* e = getenv("MCPB200_SHAPE_INLINE")) inline_shapes = atoi(e) != 0;
+    std::vector<int> used;
+    for (size_t sidx = 0; sidx < shapes.size(); ++sidx) {
+      const Shape& sh = shapes[sidx];
+      const int cnt = (int)sh.out_idx.size();
+      if (cnt < kMinShapeInstances) continue;
+      used.push_back((int)sidx);
+      const int nl = (int)sh.leaf_kind.size();
+      // a leaf whose index (or constant value) is the same in every instance becomes a literal
+      std::vector<char> uniform(nl, 1);
+      for (int k = 0; k < nl; ++k)
+        for (int q = 1; q < cnt && uniform[k]; ++q) {
+          if (sh.leaf_kind[k] == MCPB200_OP_CONST) uniform[k] = P.consts[sh.leaf_val[q][k]] == P.consts[sh.leaf_val[0][k]];
+          else uniform[k] = sh.leaf_val[q][k] == sh.leaf_val[0][k];
+        }
+      std::vector<int32_t> itab;   // [varying index leaf][instance], then the output indices
+      std::vector<double> ctab;    // [varying constant leaf][instance]
+      std::vector<int> irow(nl, -1), crow(nl, -1);
+      int ni = 0, nc = 0;
+      for (int k = 0; k < nl; ++k) {
+        if (uniform[k]) continue;
+        if (sh.leaf_kind[k] == MCPB200_OP_CONST) {
+          crow[k] = nc++;
+          for (int q = 0; q < cnt; ++q) ctab.push_back(P.consts[sh.leaf_val[q][k]]);
+        } else {
+          irow[k] = ni++;
+          for (int q = 0; q < cnt; ++q) itab.push_back((int32_t)sh.leaf_val[q][k]);
+        }
+      }
+      for (int q = 0; q < cnt; ++q) itab.push_back(sh.out_idx[q]);
+      const std::string fn = name + "_s" + std::to_string(sidx);
+      emit_table(os, "int", (fn + "_I").c_str(), itab);
+      if (nc) emit_table(os, "double", (fn + "_C").c_str(), ctab, true);
+      os << "__device__ " << (inline_shapes ? "__forceinline__" : "__noinline__") << " void " << fn << "(int lane, " << params << ") {\n";
+      os << "#pragma unroll 1\n  for (int q = lane; q < " << cnt << "; q += " << max_parts << ") {\n";
+      auto leaf_expr = [&](int k) -> std::string {
+        const char* arr = sh.leaf_kind[k] == MCPB200_OP_X ? "x" : sh.leaf_kind[k] == MCPB200_OP_Y ? "y" : "th";
+        if (sh.leaf_kind[k] == MCPB200_OP_CONST)
+          return uniform[k] ? "(" + dlit(P.consts[sh.leaf_val[0][k]]) + ")" : fn + "_C[" + std::to_string(crow[k] * cnt) + " + q]";
+        if (uniform[k]) return std::string(arr) + "[" + std::to_string(sh.leaf_val[0][k]) + "]";
+        return std::string(arr) + "[" + fn + "_I[" + std::to_string(irow[k] * cnt) + " + q]]";
+      };
+      for (int k = 0; k < nl; ++k) os << "    const double l" << k << " = " << leaf_expr(k) << ";\n";
+      auto rf = [&](int r) -> std::string { return r < 0 ? "l" + std::to_string(-1 - r) : "n" + std::to_string(r); };
+      for (size_t i = 0; i < sh.ops.size(); ++i) {
+        const ShapeOp& o = sh.ops[i];
+        os << "    const double n" << i << " = ";
+        const std::string A = rf(o.a);
+        switch (o.op) {
+          case MCPB200_OP_ADD: os << A << " + " << rf(o.b); break;
+          case MCPB200_OP_SUB: os << A << " - " << rf(o.b); break;
+          case MCPB200_OP_MUL: os << A << " * " << rf(o.b); break;
+          case MCPB200_OP_DIV: os << A << " / " << rf(o.b); break;
+          case MCPB200_OP_NEG: os << "-" << A; break;
+          case MCPB200_OP_SQRT: os << "sqrt(" << A << ")"; break;
+          case MCPB200_OP_EXP: os << "exp(" << A << ")"; break;
+          case MCPB200_OP_LOG: os << "log(" << A << ")"; break;
+          case MCPB200_OP_SIN: os << "sin(" << A << ")"; break;
+          case MCPB200_OP_COS: os << "cos(" << A << ")"; break;
+          case MCPB200_OP_POWI: os << "mcp_powi(" << A << ", " << o.b << ")"; break;
+          default: os << "0.0"; break;
+        }
+        os << ";\n";
+      }
+      os << "    " << arrays[sh.arr] << "[" << fn << "_I[" << ni * cnt << " + q]] = " << rf(sh.root) << ";\n  }\n}\n";
+    }
+    const bool have_rest = !rest.empty();
+    if (have_rest) partitioned(os, name + "_rest", params, args, rest, max_parts, units, unit_prelude);
+    os << "// " << outs.size() << " outputs: " << (outs.size() - rest.size()) << " in " << used.size() << " shape groups, "
+       << rest.size() << " lane-partitioned\n";
+    os << "__device__ __forceinline__ void " << name << "_par(int lane, " << params << ") {\n";
+    for (int sidx : used) os << "  " << name << "_s" << sidx << "(lane, " << args << ");\n";
+    if (have_rest) os << "  " << name << "_rest_par(lane, " << args << ");\n";
+    os << "}\n";
   }
 
   void statement(std::ostringstream& os, int n) const {
@@ -1153,16 +1341,18 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   Emitter E(P);
   // residual rows [G; H] and the computed Jacobian entries, evaluated together so sub-expressions are shared
   os << "// G, H (src/mcp.jl:76-80 minus the structural slack rows) and the z/θ-dependent entries of ∇F_z\n";
+  bool use_shapes = true;   // MCPB200_SHAPES=0: lane-partitioned functions only
+  if (const char* e = getenv("MCPB200_SHAPES")) use_shapes = atoi(e) != 0;
   if (P.dense_kernel < 2) {
-    std::vector<std::pair<int32_t, std::string>> outs;
-    for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], "g[" + std::to_string(i) + "]"});
-    for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], "h[" + std::to_string(i) + "]"});
-    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], "jv[" + std::to_string(i) + "]"});
-    E.partitioned(os, "mcp_eval_newton",
-                  P.large_state ? "const double* x, const double* y, const double* th, double* g, double* h, double* jv"
-                                : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
-                                  "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
-                  "x, y, th, g, h, jv", outs, P.dense_kernel ? 256 : P.sub, &P.units, unit_prelude);
+    std::vector<Emitter::OutT> outs;
+    for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], 0, i});
+    for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], 1, i});
+    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], 2, i});
+    E.evaluation(os, "mcp_eval_newton",
+                 P.large_state ? "const double* x, const double* y, const double* th, double* g, double* h, double* jv"
+                               : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                                 "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
+                 "x, y, th, g, h, jv", outs, {"g", "h", "jv"}, P.dense_kernel ? 256 : P.sub, &P.units, unit_prelude, use_shapes);
   }
   if (P.dense_kernel >= 2) {
     os << "// G(0;θ), H(0;θ): the constant part of the (affine in z) residual\n";
@@ -1177,17 +1367,17 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
   if (P.has_jt) {
     os << "// computed entries of ∇F_z and ∇F_θ at the solution (src/AutoDiff.jl:27-37)\n";
-    std::vector<std::pair<int32_t, std::string>> outs;
-    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], "jv[" + std::to_string(i) + "]"});
-    for (int i = 0; i < njtv; ++i) outs.push_back({P.jtv_nodes[i], "jtv[" + std::to_string(i) + "]"});
+    std::vector<Emitter::OutT> outs;
+    for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], 0, i});
+    for (int i = 0; i < njtv; ++i) outs.push_back({P.jtv_nodes[i], 1, i});
     if (outs.empty()) {
       os << "__device__ __forceinline__ void mcp_eval_sens_par(int, const double*, const double*, const double*, double*, double*) {}\n";
     } else {
-      E.partitioned(os, "mcp_eval_sens",
-                    P.large_state ? "const double* x, const double* y, const double* th, double* jv, double* jtv"
-                                  : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
-                                    "double* __restrict__ jv, double* __restrict__ jtv",
-                    "x, y, th, jv, jtv", outs, P.sub, &P.units, unit_prelude);
+      E.evaluation(os, "mcp_eval_sens",
+                   P.large_state ? "const double* x, const double* y, const double* th, double* jv, double* jtv"
+                                 : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
+                                   "double* __restrict__ jv, double* __restrict__ jtv",
+                   "x, y, th, jv, jtv", outs, {"jv", "jtv"}, P.sub, &P.units, unit_prelude, use_shapes);
     }
   }
   os << kernel_template;
