@@ -168,11 +168,34 @@ def run_reference(args):
                                        f"C restatement of src/solver.jl, OpenMP over θ on {threads} threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to
+    stdout when NCCL_DEBUG=VERSION is set on the box), so fd 1 is pointed at stderr for the duration of the run and
+    the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -327,7 +350,7 @@ def main():
         if not args.no_cpu_baseline:
             cb, _ = cpu_baseline(mcp, Θ_host, min(args.cpu_sample, B))
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
