@@ -649,9 +649,9 @@ __device__ __forceinline__ double blk_ftb_linesearch(const double* RS v, const d
 //     cached H_x (4 conflict-free + 7 broadcast shared loads per 28 DFMAs);
 //   * LU with partial pivoting, one __syncthreads per column: column j lives entirely in warp j mod 16, which
 //     finds the pivot with one warp-wide max, and publishes the pivot row index and the multipliers; after the
-//     barrier every warp fetches its part of the pivot row by shuffle from lane (pivot row mod 32) and updates
-//     its columns > j (finished columns are skipped warp-uniformly).  Each warp also stores its part of the U
-//     row, transposed and in pivot order;
+//     barrier lane (pivot row mod 32) of every warp stores its part of the pivot row into Uᵀ (transposed, pivot
+//     order) and clears it in the tile, the warp reads it back as broadcasts and updates its columns > j
+//     (finished columns are skipped warp-uniformly);
 //   * back substitution is a column sweep by warp 0 alone with the right-hand side in registers (no barriers).
 // The solver logic is the same literal restatement of src/solver.jl:63-121 as in mcp_solve_kernel.
 // ------------------------------------------------------------------------------------------------

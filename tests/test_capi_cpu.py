@@ -169,3 +169,28 @@ def test_plan_variants_are_selected_and_compile(monkeypatch, tmp_path):
     monkeypatch.setenv("MCPB200_LARGE_STATE", "1")
     h = capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY)
     assert _macros(h.source())["LARGE_STATE"] == "1" and h.info()["smem_bytes_per_cta"] < 64 * 1024
+
+
+def test_shape_grouped_evaluation_and_split_compilation(monkeypatch, tmp_path):
+    """Code generation: outputs that repeat an expression shape go into lock-step shape groups (index tables), the
+    rest into lane-partitioned functions; large sets of those are compiled as separate units and linked."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    ir = problems.lane_change_game().mcp.ir
+    src = capi.Handle(ir, capi.COMPILE_ONLY).source()
+    m = re.search(r"// (\d+) outputs: (\d+) in (\d+) shape groups, (\d+) lane-partitioned", src)
+    total, shaped, groups, rest = map(int, m.groups())
+    assert total == 200 + 250 + 140 and shaped + rest == total
+    assert shaped >= 0.9 * total and groups <= 40          # 10 stages x 2 players repeat a few dozen shapes
+    assert "mcp_eval_newton_s" in src and "_I[" in src
+    # every shape group stores through its index table into one of the target arrays
+    assert len(re.findall(r"^\s+(?:g|h|jv)\[mcp_eval_newton_s\d+_I\[\d+ \+ q\]\] = ", src, flags=re.M)) == groups
+    # shapes off: everything lane-partitioned, one translation unit
+    monkeypatch.setenv("MCPB200_SHAPES", "0")
+    h = capi.Handle(ir, capi.COMPILE_ONLY)
+    assert "mcp_eval_newton_s0" not in h.source() and "mcp_eval_newton_rest_p31" in h.source()
+    assert "extern __device__ void mcp_eval_newton_rest_p0" not in h.source()
+    # ... and forced into separately compiled units: the main unit only declares the parts, nvJitLink resolves them
+    monkeypatch.setenv("MCPB200_SPLIT_COMPILE", "1")
+    h = capi.Handle(ir, capi.COMPILE_ONLY | capi.NO_CACHE)
+    assert "extern __device__ void mcp_eval_newton_rest_p0" in h.source()
+    assert "void mcp_eval_newton_rest_p0(const double* __restrict__ x" not in h.source().replace("extern __device__ void mcp_eval_newton_rest_p0(", "")
