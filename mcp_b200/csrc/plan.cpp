@@ -1092,6 +1092,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   auto warps_for = [&](int64_t doubles) {  // instances per CTA
     int64_t w = (kSmemBudget - shared_table_doubles * 8) / (doubles * 8);
     w = std::min<int64_t>(w, 768 / P.sub);   // ≤ 768 threads per CTA keeps ≥ 85 registers per thread
+    if (const char* e = getenv("MCPB200_MAX_WARPS")) w = std::min<int64_t>(w, std::max(1, atoi(e)));   // tuning: fewer instances, more L1
     if (P.sub == 16) w &= ~int64_t(1);       // whole warps
     return (int)std::max<int64_t>(0, w);
   };
