@@ -1684,6 +1684,8 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
   // boundaries, where the whole solver state is (x, y, s, ϵ, kkt_error, outer_iters)), parks the rest in
   // the output arrays and a deferred list; pass 1 (a second launch) resumes them, all long, together.
   const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+  const bool spread = p.pass && n_deferred <= (unsigned long long)gridDim.x * SOLVE_INST;
+  bool fetched = false;
 
   // solver state of my sub-warp's instance (replicated in each of its lanes)
   bool have = false, done = false, head = true, brk = false;
@@ -1697,8 +1699,13 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
     while (!done && !step) {
       if (!have) {
         unsigned long long q = 0;
-        if (sl == 0) q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
-        q = __shfl_sync(smask, q, 0, SUB);
+        if (spread) {   // pass 1 with fewer instances than slots: one per SM first (each is a long, latency-bound run)
+          q = fetched ? n_deferred : (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * slot;
+          fetched = true;
+        } else {
+          if (sl == 0) q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+          q = __shfl_sync(smask, q, 0, SUB);
+        }
         if (p.pass) {
           if (q >= n_deferred) {
             done = true;

@@ -396,6 +396,8 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
     CU_TRY(h, D.ModuleLoadData(&st->mod, h->cubin.data()));
     CU_TRY(h, D.ModuleGetFunction(&st->f_solve, st->mod, "mcp_solve_kernel"));
     CU_TRY(h, D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_solve));
+    if (const char* e = getenv("MCPB200_CARVEOUT"))   // tuning: shared-memory carve-out in percent (the rest of the 256 KB is L1)
+      D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, atoi(e));
     D.FuncGetAttribute(&st->regs_solve, CU_FUNC_ATTRIBUTE_NUM_REGS, st->f_solve);
     if (h->plan.has_jt) {
       CU_TRY(h, D.ModuleGetFunction(&st->f_sens, st->mod, "mcp_sens_kernel"));
