@@ -123,13 +123,24 @@ __device__ __forceinline__ void load_shared_tables(double* smem_base) {
   __syncthreads();
 }
 
+// Named barrier among the NW warps that share one instance (ids 1…15; id 0 is __syncthreads).
+__device__ __forceinline__ void wide_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Assembly of the condensed matrix C = G_x + tol·I − G_y D⁻¹ H_x: one value per structural non-zero
 // ("dest", sorted by row then column) into the compact L2-resident array Cval[ND].
 // ------------------------------------------------------------------------------------------------
+// With NW > 1 the NW warps of a cooperative instance share the work (lane index wrole·SUB + sl, stride NW·SUB) and
+// the phases are separated by the instance's named barrier instead of __syncwarp.
+template <int NW = 1>
 __device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
                                                 const double* RS jv, const double* RS th,
-                                                const double* RS dinv, double tol, int sl, unsigned smask) {
+                                                const double* RS dinv, double tol, int sl, unsigned smask,
+                                                int wrole = 0, int bar_id = 0) {
+  const int wl = wrole * SUB + sl;   // lane index within the instance
+  constexpr int WL = NW * SUB;
   // Constant contributions are folded into D_BASE on the host; only the z/θ/D-dependent terms remain.
 #if ASM_TWO_PHASE
   // Two phases per chunk (chunks = runs of dests whose terms fit the shared term buffer):
@@ -139,24 +150,24 @@ __device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
   for (int c = 0; c < ASM_NCHUNK; ++c) {
     const int tb = CH_T[c], te = CH_T[c + 1];
 #pragma unroll 4
-    for (int t = tb + sl; t < te; t += SUB) {
+    for (int t = tb + wl; t < te; t += WL) {
       const int4 ti = T_I[t];  // {a, b, k, -}
       double v = T_COEF[t] * opval(ti.x, jv, th);
       if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
       tmp[t - tb] = v;
     }
-    __syncwarp(smask);
-    for (int d = CH_D[c] + sl; d < CH_D[c + 1]; d += SUB) {
+    if constexpr (NW > 1) wide_bar(bar_id, NW * 32); else __syncwarp(smask);
+    for (int d = CH_D[c] + wl; d < CH_D[c + 1]; d += WL) {
       const int tp = D_TP[d];
       const int t1 = D_TP[d + 1] & 0x7fffffff;
       double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
       for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t - tb];
       __stcg(Cval + d, acc);   // streaming scratch: keep L1 for the assembly tables
     }
-    __syncwarp(smask);
+    if constexpr (NW > 1) wide_bar(bar_id, NW * 32); else __syncwarp(smask);
   }
 #else
-  for (int d = sl; d < ND; d += SUB) {
+  for (int d = wl; d < ND; d += WL) {
     const int tp = D_TP[d];
     const int t1 = D_TP[d + 1] & 0x7fffffff;
     double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
@@ -168,6 +179,7 @@ __device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
     }
     __stcg(Cval + d, acc);
   }
+  if constexpr (NW > 1) wide_bar(bar_id, NW * 32);
 #endif
 }
 
@@ -198,12 +210,56 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Returns 0, or 1 if a pivot is zero / non-finite (the reference's `:failed` retcode branch,
 // src/solver.jl:84-88).
 // ------------------------------------------------------------------------------------------------
-template <int NRHS, int WS>
+// One warp's share of the elimination sweep of the shared-memory window: column batches bi ≡ wrole (mod NW), all rows.
+template <int NRHS, int WS, int NW>
+__device__ __forceinline__ void window_sweep(double* W, const double* Wp, const double (&m)[(WR + SUB - 1) / SUB], int sl, int wrole) {
+  constexpr int RPL = (WR + SUB - 1) / SUB;
+  constexpr int NP = (WC + NRHS + 1) / 2;
+  constexpr int PB = (NP < 9) ? NP : 9;
+  const double2* Wp2 = reinterpret_cast<const double2*>(Wp);
+#pragma unroll
+  for (int b0 = 0; b0 < NP; b0 += PB) {
+    if (NW > 1 && (b0 / PB) % NW != wrole) continue;
+    double2 u[PB];
+#pragma unroll
+    for (int i = 0; i < PB; ++i)
+      if (b0 + i < NP) u[i] = Wp2[b0 + i];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      const int r = sl + SUB * k;
+      if (r < WR) {
+        double2* Wr2 = reinterpret_cast<double2*>(W + r * WS);
+        double2 a[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i)
+          if (b0 + i < NP) a[i] = Wr2[b0 + i];
+#pragma unroll
+        for (int i = 0; i < PB; ++i)
+          if (b0 + i < NP) {
+            a[i].x = fma(m[k], u[i].x, a[i].x);
+            a[i].y = fma(m[k], u[i].y, a[i].y);
+            Wr2[b0 + i] = a[i];
+          }
+      }
+    }
+  }
+}
+
+// Mailbox of a cooperative (NWIDE > 1) instance, behind its window: WR multipliers, then the command word and one
+// double argument.  Commands: p >= 0 sweep the window for pivot slot p; WIDE_EXIT; WIDE_ASSEMBLE; WIDE_EVAL.
+#define WIDE_EXIT (-1)
+#define WIDE_ASSEMBLE (-2)
+#define WIDE_EVAL (-3)
+#define WIDE_MBOX(W_, WS_) ((W_) + WR * (WS_))
+#define WIDE_CMD(W_, WS_) reinterpret_cast<volatile int*>(WIDE_MBOX(W_, WS_) + ((WR + 1) & ~1))
+#define WIDE_ARG(W_, WS_) (WIDE_MBOX(W_, WS_) + ((WR + 1) & ~1) + 1)
+
+template <int NRHS, int WS, int NW = 1>
 __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
                           double* RS sol, const int* RS rowptr,
                           const unsigned short* RS cpos, const double* RS jv,
                           const double* RS th, const double* RS dinv, double* RS stage,
-                          int sl, unsigned smask) {
+                          int sl, unsigned smask, int bar_id = 0) {
   constexpr int CPW = (WC + SUB - 1) / SUB;  // matrix positions per sl
   constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
   constexpr int WPL = (WS + SUB - 1) / SUB;
@@ -462,36 +518,26 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     // Rows with a zero multiplier (and the pivot row itself, whose multiplier is forced to zero) are
     // rewritten unchanged: no per-sl branches, 128-bit conflict-free accesses (WS ≡ 2 mod 4).
     {
-      const double2* Wp2 = reinterpret_cast<const double2*>(Wp);
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
         const int r = sl + SUB * k;
         m[k] = (r < WR && r != p) ? -(m[k] * rp) : 0.0;
       }
-#pragma unroll
-      for (int b0 = 0; b0 < NP; b0 += PB) {
-        double2 u[PB];
-#pragma unroll
-        for (int i = 0; i < PB; ++i)
-          if (b0 + i < NP) u[i] = Wp2[b0 + i];
+      if constexpr (NW > 1) {
+        // cooperative sweep: publish the pivot slot and the multipliers, all NW warps of the instance sweep their
+        // column batches between the two barriers (the helpers wait at barrier A whenever the leader is elsewhere)
+        double* mbox = WIDE_MBOX(W, WS);
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
           const int r = sl + SUB * k;
-          if (r < WR) {
-            double2* Wr2 = reinterpret_cast<double2*>(W + r * WS);
-            double2 a[PB];
-#pragma unroll
-            for (int i = 0; i < PB; ++i)
-              if (b0 + i < NP) a[i] = Wr2[b0 + i];
-#pragma unroll
-            for (int i = 0; i < PB; ++i)
-              if (b0 + i < NP) {
-                a[i].x = fma(m[k], u[i].x, a[i].x);
-                a[i].y = fma(m[k], u[i].y, a[i].y);
-                Wr2[b0 + i] = a[i];
-              }
-          }
+          if (r < WR) mbox[r] = m[k];
         }
+        if (sl == 0) WIDE_CMD(W, WS)[0] = p;
+        wide_bar(bar_id, NW * 32);
+        window_sweep<NRHS, WS, NW>(W, Wp, m, sl, 0);
+        wide_bar(bar_id, NW * 32);
+      } else {
+        window_sweep<NRHS, WS, 1>(W, Wp, m, sl, 0);
       }
 #pragma unroll
       for (int k = 0; k < RPL; ++k) {
@@ -1644,10 +1690,18 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
 // of the main loop.  The sub-warps of a warp re-align once per Newton step (the full-warp vote below),
 // so the heavy phases of their two instances execute as the same instructions.
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kernel(const SolveParams p) {
+extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_solve_kernel(const SolveParams p) {
   extern __shared__ double smem[];
+#if NWIDE > 1
+  // cooperative instances: NWIDE consecutive warps per instance, the first is the leader (runs everything below),
+  // the others only help with the window sweep of the factorisation (wide_helper)
+  const int sl = threadIdx.x & 31;
+  const int slot = (threadIdx.x >> 5) / NWIDE;
+  const int wrole = (threadIdx.x >> 5) % NWIDE;
+#else
   const int sl = threadIdx.x % SUB;
   const int slot = threadIdx.x / SUB;  // instance slot of this sub-warp within the CTA
+#endif
   const unsigned smask = sub_mask(threadIdx.x & 31);
   load_shared_tables(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
@@ -1677,6 +1731,36 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
   double* Cval = p.scratch + ((size_t)blockIdx.x * SOLVE_INST + slot) * SOLVE_SCRATCH;
   double* UT = Cval + CVAL_DOUBLES;
   const double tol = p.tol;
+#if NWIDE > 1
+  static_assert(THETA_IN_SMEM, "cooperative instances need θ at a fixed address");
+  if (wrole != 0) {
+    // Helper warps: wait for the leader's command, do their share, report back (see WIDE_* above).  They sit at
+    // barrier A whenever the leader is in a phase that is not shared.
+    constexpr int RPL = (WR + SUB - 1) / SUB;
+    const int bar_id = 1 + slot;
+    for (;;) {
+      wide_bar(bar_id, NWIDE * 32);   // A: command published
+      const int c = WIDE_CMD(W, WS1)[0];
+      if (c == WIDE_EXIT) return;
+      if (c == WIDE_ASSEMBLE) {
+        assemble_matrix<NWIDE>(Cval, W, jv, th, dinv, *WIDE_ARG(W, WS1), sl, smask, wrole, bar_id);   // ends with a barrier
+      } else if (c == WIDE_EVAL) {
+        mcp_eval_newton_par(wrole * 32 + sl, x, y, th, g, hh, jv);
+        wide_bar(bar_id, NWIDE * 32);   // B
+      } else {
+        double m[RPL];
+        const double* mbox = WIDE_MBOX(W, WS1);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+          const int r = sl + SUB * k;
+          m[k] = (r < WR) ? mbox[r] : 0.0;
+        }
+        window_sweep<1, WS1, NWIDE>(W, W + c * WS1, m, sl, wrole);
+        wide_bar(bar_id, NWIDE * 32);   // B: sweep complete
+      }
+    }
+  }
+#endif
 
   // Scheduling (semantics-neutral): instances that never converge run ~30x longer than the rest (up to
   // (max_outer-1)(max_inner-1) Newton steps) and would leave most of the GPU idle behind a long tail.
@@ -1797,8 +1881,15 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
 
     // ---- one Newton step (src/solver.jl:76-108) -------------------------------------------------------------
     // F and the Jacobian entries at the current iterate (:79-80); lane i evaluates output group i
+#if NWIDE > 1
+    if (sl == 0) WIDE_CMD(W, WS1)[0] = WIDE_EVAL;
+    wide_bar(1 + slot, NWIDE * 32);
+    mcp_eval_newton_par(sl, x, y, th, g, hh, jv);
+    wide_bar(1 + slot, NWIDE * 32);
+#else
     mcp_eval_newton_par(sl, x, y, th, g, hh, jv);
     __syncwarp(smask);
+#endif
     double fmax_ = 0.0;
     for (int i = sl; i < NX; i += SUB) fmax_ = nanmax(fmax_, fabs(g[i]));
     for (int k = sl; k < NY; k += SUB) {
@@ -1820,9 +1911,18 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
       sol[i] = r;
     }
     __syncwarp(smask);  // G (aliased onto the window) is dead from here on: the window becomes scratch
+#if NWIDE > 1
+    if (sl == 0) {
+      *WIDE_ARG(W, WS1) = tol;
+      WIDE_CMD(W, WS1)[0] = WIDE_ASSEMBLE;
+    }
+    wide_bar(1 + slot, NWIDE * 32);
+    assemble_matrix<NWIDE>(Cval, W, jv, th, dinv, tol, sl, smask, 0, 1 + slot);
+#else
     assemble_matrix(Cval, W, jv, th, dinv, tol, sl, smask);
     __syncwarp(smask);
-    bool failed = band_solve<1, WS1>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SOLVE_OFF_STAGE, sl, smask) != 0;  // :84-88
+#endif
+    bool failed = band_solve<1, WS1, NWIDE>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SOLVE_OFF_STAGE, sl, smask, 1 + slot) != 0;  // :84-88
     double a_s = 1.0, a_y = 1.0;
     if (!failed) {
       // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
@@ -1855,6 +1955,12 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST, 1) mcp_solve_kern
     }
     __syncwarp(smask);
   }
+#if NWIDE > 1
+  {   // release this instance slot's helper warps
+    if (sl == 0) WIDE_CMD(W, WS1)[0] = WIDE_EXIT;
+    wide_bar(1 + slot, NWIDE * 32);
+  }
+#endif
 }
 
 #endif  // DENSE_KERNEL

@@ -277,12 +277,15 @@ JitLink& jitlink() {
 }
 
 // One NVRTC compilation to a cubin (relocatable when `rdc`).  Returns an empty string on success, else the log.
-std::string nvrtc_to_cubin(const std::string& src, const std::string& name, bool rdc, bool lineinfo, std::vector<char>& cubin) {
+std::string nvrtc_to_cubin(const std::string& src, const std::string& name, bool rdc, bool lineinfo, std::vector<char>& cubin,
+                           int maxreg = 0) {
   nvrtcProgram prog;
   if (nvrtcCreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) return "nvrtcCreateProgram failed";
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
   if (lineinfo) opts.push_back("-lineinfo");
   if (rdc) opts.push_back("--relocatable-device-code=true");
+  const std::string mr = "--maxrregcount=" + std::to_string(maxreg);
+  if (maxreg > 0) opts.push_back(mr.c_str());
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;
@@ -332,12 +335,17 @@ int compile_source(mcpb200_problem* h, uint32_t flags) {
     std::atomic<size_t> next{0};
     unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)(nu + 1)));
     if (const char* e = getenv("MCPB200_COMPILE_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+    // separately compiled functions do not see the kernels' launch bounds: cap their registers at what the widest
+    // kernel of this plan may use
+    const Plan& P = h->plan;
+    const int threads = std::max({P.dense_kernel ? P.dense_threads : P.sub * P.ipc_solve * P.nwide, P.has_jt ? P.sub * P.ipc_sens : 0, 32});
+    const int maxreg = std::min(255, (65536 / threads) / 8 * 8);
     auto worker = [&] {
       for (;;) {
         const size_t i = next.fetch_add(1);
         if (i > nu) break;
         errs[i] = (i == 0) ? nvrtc_to_cubin(src, cu_path, true, true, objs[0])
-                           : nvrtc_to_cubin(units[i - 1], cu_path + ".unit" + std::to_string(i - 1), true, false, objs[i]);  // (sources of the units are not kept: no line info)
+                           : nvrtc_to_cubin(units[i - 1], cu_path + ".unit" + std::to_string(i - 1), true, false, objs[i], maxreg);  // (sources of the units are not kept: no line info)
       }
     };
     std::vector<std::thread> pool;
@@ -423,7 +431,7 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   const long long ctas_needed = (p.B + P.ipc_solve - 1) / P.ipc_solve;
   const long long max_ctas = (long long)st->num_sms * (P.dense_kernel ? P.dense_ctas_per_sm : 1);
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
-  const unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve);
+  const unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve * P.nwide);
   const size_t scratch_bytes = (size_t)st->num_sms * P.ipc_solve * P.scratch_doubles_solve * 8;
   if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * P.ipc_sens * P.scratch_doubles_sens * 8)))
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
@@ -603,7 +611,7 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->n_jac_constant = P.n_const_entries;
   info->n_assembly_dests = (int)P.d_row.size();
   info->n_assembly_terms = (int)P.t_coef.size();
-  info->threads_per_instance = P.dense_kernel ? P.dense_threads : P.sub;
+  info->threads_per_instance = P.dense_kernel ? P.dense_threads : P.sub * P.nwide;
   info->instances_per_cta = P.ipc_solve;
   info->ctas_per_sm = P.dense_kernel ? P.dense_ctas_per_sm : 1;
   info->smem_bytes_per_cta = (int)P.smem_solve;

@@ -1045,7 +1045,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
     const int es = (pw * npart + nrhs + 3) & ~1;
     const bool regwin = P.regwin && P.R <= P.sub && pw <= 40;
-    if (!regwin) return (int64_t)P.R * ws;
+    if (!regwin) return (int64_t)P.R * ws + even(P.R) + 4;                 // + mailbox of the cooperative sweep (NWIDE)
     int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
     w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
     w = std::max<int64_t>(w, std::min<int64_t>(nterms_all, kAsmChunk));     // two-phase assembly buffer (chunked)
@@ -1121,6 +1121,20 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (P.large_state) {
     P.ipc_solve = std::min(P.ipc_solve, ls_cap);
     P.ipc_sens = std::min(P.ipc_sens, ls_cap);
+  }
+  // Big shared-memory windows (the masked games): one warp per instance leaves the SM at 3–8 warps and every pivot
+  // step is a long dependent sweep; NWIDE warps then share the sweep of one instance (column batches round-robin),
+  // the instance's other phases stay on its leader warp.  MCPB200_NWIDE overrides.
+  P.nwide = 1;
+  if (!P.dense_kernel && P.sub == 32 && P.ipc_solve >= 1 && P.theta_in_smem) {
+    const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
+    const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
+    const bool regwin_used = P.regwin && P.R <= P.sub && pw <= 40;
+    const int np = (P.WC + 1 + 1) / 2, pb = std::min(np, 9), nbatch = (np + pb - 1) / pb;
+    if (!regwin_used && !P.dense_schur) {
+      P.nwide = std::max(1, std::min({4, 16 / P.ipc_solve, nbatch}));
+      if (const char* e = getenv("MCPB200_NWIDE")) P.nwide = std::max(1, std::min({atoi(e), nbatch, 32 / P.ipc_solve}));
+    }
   }
   if (P.ipc_solve < 1) {
     char buf[200];
@@ -1281,6 +1295,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
+  os << "#define NWIDE " << P.nwide << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
@@ -1353,7 +1368,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                  P.large_state ? "const double* x, const double* y, const double* th, double* g, double* h, double* jv"
                                : "const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ th, "
                                  "double* __restrict__ g, double* __restrict__ h, double* __restrict__ jv",
-                 "x, y, th, g, h, jv", outs, {"g", "h", "jv"}, P.dense_kernel ? 256 : P.sub, &P.units, unit_prelude, use_shapes);
+                 "x, y, th, g, h, jv", outs, {"g", "h", "jv"}, P.dense_kernel ? 256 : P.sub * P.nwide, &P.units, unit_prelude, use_shapes);
   }
   if (P.dense_kernel >= 2) {
     os << "// G(0;θ), H(0;θ): the constant part of the (affine in z) residual\n";
