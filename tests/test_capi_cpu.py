@@ -194,3 +194,19 @@ def test_shape_grouped_evaluation_and_split_compilation(monkeypatch, tmp_path):
     h = capi.Handle(ir, capi.COMPILE_ONLY | capi.NO_CACHE)
     assert "extern __device__ void mcp_eval_newton_rest_p0" in h.source()
     assert "void mcp_eval_newton_rest_p0(const double* __restrict__ x" not in h.source().replace("extern __device__ void mcp_eval_newton_rest_p0(", "")
+
+
+def test_cooperative_instances_are_planned_for_big_windows(monkeypatch, tmp_path):
+    """Plans whose window stays in shared memory (too wide for the register layout) get NWIDE warps per instance;
+    register-window plans and tiny problems keep one (sub-)warp per instance."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
+    m = _macros(h.source())
+    assert (m["NWIDE"], m["LARGE_STATE"], m["SUB"]) == ("2", "1", "32")
+    assert h.info()["threads_per_instance"] == 64 and h.info()["instances_per_cta"] == 8
+    assert "WIDE_ASSEMBLE" in h.source()
+    assert _macros(capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY).source())["NWIDE"] == "1"
+    assert _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())["NWIDE"] == "1"
+    monkeypatch.setenv("MCPB200_NWIDE", "1")
+    h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["NWIDE"] == "1" and h.info()["threads_per_instance"] == 32
