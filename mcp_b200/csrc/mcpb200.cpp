@@ -338,7 +338,9 @@ int compile_source(mcpb200_problem* h, uint32_t flags) {
     // separately compiled functions do not see the kernels' launch bounds: cap their registers at what the widest
     // kernel of this plan may use
     const Plan& P = h->plan;
-    const int threads = std::max({P.dense_kernel ? P.dense_threads : P.sub * P.ipc_solve * P.nwide, P.has_jt ? P.sub * P.ipc_sens : 0, 32});
+    // (dense kernels v1/v2 are compiled for two CTAs per SM: __launch_bounds__(256, 2))
+    const int dense_resident = P.dense_threads * ((P.dense_kernel == 1 || P.dense_kernel == 2) ? 2 : 1);
+    const int threads = std::max({P.dense_kernel ? dense_resident : P.sub * P.ipc_solve * P.nwide, P.has_jt ? P.sub * P.ipc_sens : 0, 32});
     const int maxreg = std::min(255, (65536 / threads) / 8 * 8);
     auto worker = [&] {
       for (;;) {

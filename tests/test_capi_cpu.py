@@ -210,3 +210,12 @@ def test_cooperative_instances_are_planned_for_big_windows(monkeypatch, tmp_path
     monkeypatch.setenv("MCPB200_NWIDE", "1")
     h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
     assert _macros(h.source())["NWIDE"] == "1" and h.info()["threads_per_instance"] == 32
+
+
+def test_split_units_respect_the_kernels_register_budget(monkeypatch, tmp_path):
+    """Separately compiled evaluation units do not see the kernels' launch bounds; the runtime caps their registers
+    so that nvJitLink accepts them (a 256-thread, 2-CTA/SM dense kernel may call only ≤128-register functions)."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    h = capi.Handle(problems.random_qp(111, 128).ir, capi.COMPILE_ONLY)     # too big for the register-tiled kernel
+    assert h.info()["threads_per_instance"] == 256
+    assert "extern __device__ void mcp_eval_newton_rest_p0" in h.source()    # its evaluation is split into units
