@@ -115,9 +115,17 @@ __device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, F
 // CTA-shared tables (first SHARED_TABLE_DOUBLES doubles of dynamic shared memory): ROWPTR_S[NRED+1]
 // (first dest of each condensed row) and CPOS_S[ND] (circular window position of each dest).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_shared_tables(double* smem_base) {
+__device__ __forceinline__ void load_shared_tables(double* smem_base, bool transposed = false) {
   int* rowptr = reinterpret_cast<int*>(smem_base);
   unsigned short* cpos = reinterpret_cast<unsigned short*>(rowptr + NRED + 1);
+#if HAS_ADJOINT
+  if (transposed) {   // the column-major view of the same non-zeros: the factorisation then sees Cᵀ
+    for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = DT_ROWPTR[i];
+    for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)DT_CPOS[i];
+    __syncthreads();
+    return;
+  }
+#endif
   for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = D_ROWPTR[i];
   for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)D_CPOS[i];
   __syncthreads();
@@ -259,7 +267,10 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
                           double* RS sol, const int* RS rowptr,
                           const unsigned short* RS cpos, const double* RS jv,
                           const double* RS th, const double* RS dinv, double* RS stage,
-                          int sl, unsigned smask, int bar_id = 0) {
+                          int sl, unsigned smask, int bar_id = 0, const int* RS src = nullptr) {
+  // `src` (adjoint solves): dest e of the row tables is Cval[src[e]] — with the column-major tables the window then
+  // holds Cᵀ without re-assembling anything
+  auto cval_at = [&](int e) -> double { return __ldcg(Cval + (src ? src[e] : e)); };
   constexpr int CPW = (WC + SUB - 1) / SUB;  // matrix positions per sl
   constexpr int RPL = (WR + SUB - 1) / SUB;  // row slots per sl
   constexpr int WPL = (WS + SUB - 1) / SUB;
@@ -293,7 +304,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     for (int r = 0; r < WR; ++r) {  // rows 0 … WR-1, relative to column 0 (their columns are < WC: no wrap)
       for (int q = sl; q < ES; q += SUB) E[q] = 0.0;
       __syncwarp(smask);
-      for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = __ldcg(Cval + e);
+      for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = cval_at(e);
       if (sl < NRHS) E[WCP + sl] = sol[sl * NRED + r];
       __syncwarp(smask);
       if (active && row == r) {
@@ -323,7 +334,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
         const int e = e0 + sl + SUB * k;
-        pre[k] = (e < e1) ? __ldcg(Cval + e) : 0.0;
+        pre[k] = (e < e1) ? cval_at(e) : 0.0;
       }
       for (int q = sl; q < ES; q += SUB) Eb[q] = 0.0;
       // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, row in the low byte ----
@@ -408,7 +419,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   for (int i = sl; i < WR * WS; i += SUB) W[i] = 0.0;
   __syncwarp(smask);
   for (int r = 0; r < WR; ++r) {
-    for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) W[r * WS + cpos[e]] = __ldcg(Cval + e);
+    for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) W[r * WS + cpos[e]] = cval_at(e);
     if (sl < NRHS) W[r * WS + WC + sl] = sol[sl * NRED + r];
   }
   __syncwarp(smask);
@@ -469,7 +480,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
 #pragma unroll
     for (int k = 0; k < CPW; ++k) {
       const int e = e0 + sl + SUB * k;
-      pre[k] = (e < e1) ? __ldcg(Cval + e) : 0.0;   // written with st.cg: must not be served from a stale L1 line
+      pre[k] = (e < e1) ? cval_at(e) : 0.0;   // written with st.cg: must not be served from a stale L1 line
     }
 
     // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, slot in the low byte ----
@@ -1970,12 +1981,18 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 // through the same condensation with D = S Y⁻¹, NRHS_SENS right-hand sides per factorisation pass.
 // ------------------------------------------------------------------------------------------------
 #if HAS_JT
+#ifndef USE_ADJOINT
+#define USE_ADJOINT 1
+#endif
 extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel(const SensParams p) {
   extern __shared__ double smem[];
   const int sl = threadIdx.x % SUB;
   const int slot = threadIdx.x / SUB;
   const unsigned smask = sub_mask(threadIdx.x & 31);
-  load_shared_tables(smem);
+  // Pullback only (z̄ → θ̄): adjoint mode — ONE solve with Cᵀ per instance instead of one solve of C per column of
+  // ∇F_θ (nθ = 160 for the masked game at N = 10).  The Jacobian and the pushforward keep the forward solves.
+  const bool adjoint = HAS_ADJOINT && USE_ADJOINT && p.zbar && p.thetabar && !p.dzdtheta && !p.z_p;
+  load_shared_tables(smem, adjoint);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
   double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SENS_SMEM_DOUBLES;
@@ -2024,6 +2041,44 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
       for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = 0.0;
     __syncwarp(smask);
     int bad = 0;
+#if HAS_ADJOINT && USE_ADJOINT
+    if (adjoint) {
+      // Jᵀλ = z̄ condensed like the forward system:  Cᵀ λ₁ = x̄ − H_xᵀ v,  v = D⁻¹ȳ − s̄,
+      // λ₂ = v − D⁻¹ G_yᵀ λ₁,  θ̄ = −∇F_θᵀ [λ₁; λ₂]   (the complementarity rows do not depend on θ)
+      const double* zb = p.zbar + inst * NZ;
+      for (int k = sl; k < NY; k += SUB) wq[k] = dinv[k] * zb[NX + k] - zb[NX + NY + k];
+      for (int i = sl; i < NRED; i += SUB) sol[i] = zb[PERM[i]];
+      __syncwarp(smask);
+      for (int k = sl; k < NY; k += SUB) {
+        const double vk = wq[k];
+        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) atomicAdd(&sol[H_COL[e]], -H_COEF[e] * opval(H_CODE[e], jv, th) * vk);
+      }
+      __syncwarp(smask);
+      assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
+      __syncwarp(smask);
+      bad = band_solve<1, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask, 0, DT_SRC);
+      if (!bad) {
+        for (int i = sl; i < NRED; i += SUB) {
+          const double li = sol[i];
+          for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
+            atomicAdd(&wq[R_K[e]], -dinv[R_K[e]] * R_COEF[e] * opval(R_CODE[e], jv, th) * li);
+        }
+        __syncwarp(smask);
+        for (int q = sl; q < NT; q += SUB) {
+          double acc = 0.0;
+          for (int e = Q_PTR[q]; e < Q_PTR[q + 1]; ++e) {
+            const int row = Q_ROW[e];
+            const double lam = (row < NX) ? sol[IPERM[row]] : wq[row - NX];
+            acc -= Q_COEF[e] * opval(Q_CODE[e], jtv, th) * lam;
+          }
+          p.thetabar[inst * NT + q] = acc;
+        }
+      }
+      if (sl == 0 && p.status_out) p.status_out[inst] = bad;
+      __syncwarp(smask);
+      continue;
+    }
+#endif
     for (int q0 = 0; q0 < NT; q0 += NRHS_SENS) {
       const int nq = min(NRHS_SENS, NT - q0);
       for (int i = sl; i < NRHS_SENS * NY; i += SUB) wq[i] = 0.0;

@@ -931,6 +931,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     P.d_tptr.push_back(0);
     for (auto& dd : ds) {
       P.d_row.push_back(dd.row);
+      P.d_col.push_back(dd.col);
       P.d_cpos.push_back(dd.col % P.WC);
       P.d_diag.push_back(dd.row == dd.col);
       double base = 0.0;
@@ -1311,6 +1312,27 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     emit_table(os, "int", "D_CPOS", P.d_cpos);
     emit_table(os, "int", "D_TP", tp);
     emit_table(os, "double", "D_BASE", P.d_base, true);
+    // Adjoint sensitivities (θ̄ from z̄ with ONE solve of Cᵀ instead of nθ solves of C): the same non-zeros in
+    // column-major order — first dest of each column, window position of its row, index into Cval.
+    const bool adjoint = P.has_jt && !P.dense_schur && !P.dense_kernel && P.kl == P.ku;
+    os << "#define HAS_ADJOINT " << (adjoint ? 1 : 0) << "\n";
+    if (adjoint) {
+      std::vector<int32_t> ord(P.d_row.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int32_t)i;
+      std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+        return P.d_col[a] != P.d_col[b] ? P.d_col[a] < P.d_col[b] : P.d_row[a] < P.d_row[b];
+      });
+      std::vector<int32_t> tptr(N + 1, 0), tcpos(ord.size()), tsrc(ord.size());
+      for (size_t e = 0; e < ord.size(); ++e) {
+        tptr[P.d_col[ord[e]] + 1]++;
+        tcpos[e] = P.d_row[ord[e]] % P.WC;
+        tsrc[e] = ord[e];
+      }
+      for (int i = 0; i < N; ++i) tptr[i + 1] += tptr[i];
+      emit_table(os, "int", "DT_ROWPTR", tptr);
+      emit_table(os, "int", "DT_CPOS", tcpos);
+      emit_table(os, "int", "DT_SRC", tsrc);
+    }
   }
   emit_table(os, "double", "T_COEF", P.t_coef, true);
   {

@@ -53,7 +53,7 @@ struct Plan {
   int WS1 = 0, WSS = 0;               // window row stride (doubles) for the solve / sensitivity kernels
 
   // dest d: row d_row[d] (new ordering), circular column position d_cpos[d]; terms [d_tptr[d], d_tptr[d+1])
-  std::vector<int32_t> d_row, d_cpos, d_tptr, d_diag;
+  std::vector<int32_t> d_row, d_col, d_cpos, d_tptr, d_diag;
   std::vector<double> d_base;        // numeric-constant part of each dest, folded on the host
   // term t: value = t_coef · val(t_a) · (t_k >= 0 ? dinv[t_k] · val(t_b) : 1)
   std::vector<double> t_coef;

@@ -134,6 +134,31 @@ def test_sensitivities_lane_change(lane_game):
     assert checked >= 4
 
 
+def test_adjoint_pullback_matches_forward(monkeypatch):
+    """The pullback runs in adjoint mode (one solve with Cᵀ per instance); the forward mode (one solve of C per column
+    of ∇F_θ, the structure of `src/AutoDiff.jl:18-40,59-76`) is kept behind a build switch.  Both must give the same
+    θ̄ — on the masked game (nθ = 40: 40 factorisations vs 1) and on the lane-change game."""
+    from mcp_b200 import solve_pullback
+
+    def pull(make, Θ, x0, tol, mode):
+        monkeypatch.setenv("MCPB200_DEFS", "USE_ADJOINT=" + mode)
+        mcp = make()
+        sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=tol)
+        return sol, solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, 0.5 * sol.s)
+
+    Θ = problems.masked_game_thetas(32, 4, seed=3)
+    x0 = problems.masked_game_x0(Θ, 4, 30)
+    cases = [(lambda: problems.masked_game(4, 30).mcp, Θ, x0, 1e-4),
+             (lambda: problems.lane_change_game().mcp, problems.lane_change_thetas(64, seed=5, moving=True), None, 1e-6)]
+    for make, Θc, x0c, tol in cases:
+        sol, ga = pull(make, Θc, x0c, tol, "1")
+        _, gf = pull(make, Θc, x0c, tol, "0")
+        ok = sol.status == 0
+        assert ok.sum() >= 0.8 * Θc.shape[1]
+        rel = np.max(np.abs(ga[:, ok] - gf[:, ok]), axis=0) / np.maximum(1.0, np.max(np.abs(gf[:, ok]), axis=0))
+        assert rel.max() < SENS_TOL, rel.max()
+
+
 def test_sensitivities_degenerate_backward_error(lane_game):
     """On the benchmark's own θ (zero velocity on the v_y ≥ 0 bound) ∇F_z is numerically singular, so two
     exact solvers need not agree entry-wise; what must hold is a small backward error of
