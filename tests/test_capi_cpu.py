@@ -219,3 +219,29 @@ def test_split_units_respect_the_kernels_register_budget(monkeypatch, tmp_path):
     h = capi.Handle(problems.random_qp(111, 128).ir, capi.COMPILE_ONLY)     # too big for the register-tiled kernel
     assert h.info()["threads_per_instance"] == 256
     assert "extern __device__ void mcp_eval_newton_rest_p0" in h.source()    # its evaluation is split into units
+
+
+def test_adjoint_tables_are_a_column_major_view_of_the_dests(monkeypatch, tmp_path):
+    """Adjoint pullback: DT_SRC permutes the assembled non-zeros into column-major order, DT_ROWPTR/DT_CPOS describe
+    the transposed matrix to the factorisation (same band: the plan requires kl == ku)."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    src = capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY).source()
+    m = _macros(src)
+    assert m["HAS_ADJOINT"] == "1" and m["KL"] == m["KU"]
+
+    def table(name):
+        body = re.search(r"__device__ const int %s\[\d+\] = \{([^}]*)\}" % name, src).group(1)
+        return np.array([int(v) for v in body.replace("\n", "").split(",")])
+
+    nd, n, wc = int(m["ND"]), int(m["NRED"]), int(m["WC"])
+    rowptr, cpos, tptr, tcpos, tsrc = (table(t) for t in ("D_ROWPTR", "D_CPOS", "DT_ROWPTR", "DT_CPOS", "DT_SRC"))
+    assert sorted(tsrc.tolist()) == list(range(nd)) and tptr[0] == 0 and tptr[-1] == nd and len(tptr) == n + 1
+    row_of = np.repeat(np.arange(n), np.diff(rowptr))              # row of every dest in row-major order
+    for c in range(n):                                             # column c of C = row c of Cᵀ
+        e = np.arange(tptr[c], tptr[c + 1])
+        assert np.all(cpos[tsrc[e]] == c % wc)                     # ... really are the entries of column c
+        assert np.all(tcpos[e] == row_of[tsrc[e]] % wc)            # ... placed at their row's window position
+        assert np.all(np.diff(row_of[tsrc[e]]) > 0)
+    # no sensitivities compiled in => no adjoint tables
+    src2 = capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY).source()
+    assert _macros(src2)["HAS_ADJOINT"] == "0" and "const int DT_SRC[" not in src2
