@@ -1984,6 +1984,9 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 #ifndef USE_ADJOINT
 #define USE_ADJOINT 1
 #endif
+#ifndef USE_DIRECT_JVP
+#define USE_DIRECT_JVP 1
+#endif
 extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel(const SensParams p) {
   extern __shared__ double smem[];
   const int sl = threadIdx.x % SUB;
@@ -2073,6 +2076,58 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
           }
           p.thetabar[inst * NT + q] = acc;
         }
+      }
+      if (sl == 0 && p.status_out) p.status_out[inst] = bad;
+      __syncwarp(smask);
+      continue;
+    }
+#endif
+#if USE_DIRECT_JVP
+    if (p.z_p && !p.dzdtheta && !p.zbar) {
+      // Pushforward only (θ_p → z_p, the Dual overload): the tangents are the right-hand sides — r = −∇F_θ θ_p, one
+      // solve of C per tangent (NRHS_SENS at a time) instead of one per column of ∇F_θ followed by a contraction
+      for (int p0 = 0; p0 < p.P; p0 += NRHS_SENS) {
+        const int np = min(NRHS_SENS, p.P - p0);
+        for (int i = sl; i < NRHS_SENS * NY; i += SUB) wq[i] = 0.0;
+        for (int i = sl; i < NRHS_SENS * NRED; i += SUB) sol[i] = 0.0;
+        assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
+        __syncwarp(smask);
+        for (int q = 0; q < NT; ++q) {
+          for (int e = Q_PTR[q] + sl; e < Q_PTR[q + 1]; e += SUB) {   // rows within one column are distinct: no atomics
+            const double f = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
+            const int row = Q_ROW[e];
+            for (int rp = 0; rp < np; ++rp) {
+              const double v = f * p.theta_p[(inst * p.P + p0 + rp) * NT + q];
+              if (row < NX) sol[rp * NRED + IPERM[row]] += v;
+              else wq[rp * NY + (row - NX)] += dinv[row - NX] * v;
+            }
+          }
+          __syncwarp(smask);   // the next column may touch the same rows from other lanes
+        }
+        for (int i = sl; i < NRED; i += SUB)
+          for (int rp = 0; rp < np; ++rp) {
+            double r = sol[rp * NRED + i];
+            for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * wq[rp * NY + R_K[e]];
+            sol[rp * NRED + i] = r;
+          }
+        __syncwarp(smask);
+        if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask)) {
+          bad = 1;
+          break;
+        }
+        for (int rp = 0; rp < np; ++rp) {
+          const double* so = sol + rp * NRED;
+          double* zp = p.z_p + (inst * p.P + p0 + rp) * NZ;
+          for (int c = sl; c < NRED; c += SUB) zp[PERM[c]] = so[c];
+          for (int k = sl; k < NY; k += SUB) {
+            double hx = 0.0;
+            for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * so[H_COL[e]];
+            const double zy = wq[rp * NY + k] - dinv[k] * hx;
+            zp[NX + k] = zy;
+            zp[NX + NY + k] = -s[k] * zy / y[k];
+          }
+        }
+        __syncwarp(smask);
       }
       if (sl == 0 && p.status_out) p.status_out[inst] = bad;
       __syncwarp(smask);

@@ -159,6 +159,25 @@ def test_adjoint_pullback_matches_forward(monkeypatch):
         assert rel.max() < SENS_TOL, rel.max()
 
 
+def test_pushforward_matches_jacobian_contraction(lane_game):
+    """The Dual overload's z_p = ∂z/∂θ · θ_p (`src/AutoDiff.jl:98`) is computed with the tangents as right-hand sides
+    (one solve per tangent); it must equal the contraction of the full Jacobian, for several tangents at once."""
+    from mcp_b200 import solve_jacobian_θ, solve_pushforward
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(16, seed=5, moving=True)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    J = solve_jacobian_θ(mcp, sol, Θ)                                  # n × nθ × B
+    rng = np.random.default_rng(0)
+    θp = rng.standard_normal((10, 3, Θ.shape[1]))                      # nθ × P × B
+    xp, yp, sp = solve_pushforward(mcp, sol, Θ, θp)
+    zp = np.concatenate([xp, yp, sp], axis=0)                          # n × P × B
+    ok = np.nonzero(sol.status == 0)[0]
+    assert len(ok) >= 8
+    for b in ok:
+        ref = J[:, :, b] @ θp[:, :, b]
+        assert np.max(np.abs(zp[:, :, b] - ref)) / max(1.0, np.max(np.abs(ref))) < SENS_TOL
+
+
 def test_sensitivities_degenerate_backward_error(lane_game):
     """On the benchmark's own θ (zero velocity on the v_y ≥ 0 bound) ∇F_z is numerically singular, so two
     exact solvers need not agree entry-wise; what must hold is a small backward error of
