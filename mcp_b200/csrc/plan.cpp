@@ -1053,7 +1053,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     if (nx <= 1024) w = std::max<int64_t>(w, nx);                          // G alias
     return w;
   };
-  const int64_t win_solve = window_doubles(P.WS1, 1), win_sens = window_doubles(P.WSS, P.nrhs_sens);
+  const int64_t win_solve = window_doubles(P.WS1, 1);
+  int64_t win_sens = window_doubles(P.WSS, P.nrhs_sens);
   // G is consumed (residual norm, condensed rhs) before the window is used, so it shares the window's
   // storage whenever it fits; H[k] is consumed by the very lane/iteration that writes w[k], so H lives in w.
   const bool g_alias = win_solve >= nx;
@@ -1074,20 +1075,24 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   lay << "#define SOLVE_G_IN_WIN " << (g_alias ? 1 : 0) << "\n";
   place("SOLVE_OFF_WIN", win_solve);
   int64_t solve_doubles = off;
-  off = 0;
-  place("SENS_OFF_X", nx);
-  place("SENS_OFF_Y", ny);
-  place("SENS_OFF_S", ny);
-  place("SENS_OFF_JV", njv);
-  place("SENS_OFF_JTV", njtv);
-  place("SENS_OFF_DINV", ny);
-  place("SENS_OFF_WQ", (int64_t)P.nrhs_sens * ny);
-  place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
-  if (P.theta_in_smem) place("SENS_OFF_TH", nt);
-  place("SENS_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
-  const int64_t sens_state = off;
-  place("SENS_OFF_WIN", win_sens);
-  int64_t sens_doubles = off;
+  int64_t sens_state = 0, sens_doubles = 0;
+  auto layout_sens = [&]() {
+    off = 0;
+    place("SENS_OFF_X", nx);
+    place("SENS_OFF_Y", ny);
+    place("SENS_OFF_S", ny);
+    place("SENS_OFF_JV", njv);
+    place("SENS_OFF_JTV", njtv);
+    place("SENS_OFF_DINV", ny);
+    place("SENS_OFF_WQ", (int64_t)P.nrhs_sens * ny);
+    place("SENS_OFF_SOL", (int64_t)P.nrhs_sens * N);
+    if (P.theta_in_smem) place("SENS_OFF_TH", nt);
+    place("SENS_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
+    sens_state = off;
+    place("SENS_OFF_WIN", win_sens);
+    sens_doubles = off;
+  };
+  layout_sens();
   const int64_t nd = (int64_t)P.d_row.size();
   const int64_t shared_table_doubles = even(((int64_t)(N + 1) * 4 + nd * 2 + 7) / 8);
   auto warps_for = [&](int64_t doubles) {  // instances per CTA
@@ -1110,6 +1115,20 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     // SM with its state in shared memory and 8 without (measured: solves +27 %, pullbacks 4.2x)
     if (w_std < 1 || (w_std < 4 && w_ls >= 2 * w_std)) P.large_state = 1;
     if (const char* e = getenv("MCPB200_LARGE_STATE")) P.large_state = atoi(e) != 0;
+  }
+  if (P.large_state && P.has_jt && !P.dense_kernel) {
+    // with the state out of shared memory the right-hand sides per factorisation pass are limited by the window alone
+    // (the count above was sized for vectors in shared memory: 1 for the masked games, i.e. one factorisation per
+    // column of ∇F_θ for a full Jacobian)
+    int r = std::max(1, std::min(nt, kMaxSensRhs));
+    const int want = std::max(1, std::min(ls_cap, warps_for(even(win_sens))));
+    while (r > P.nrhs_sens && warps_for(even(window_doubles(stride_for(P.WC + r), r))) < want) r /= 2;
+    if (r > P.nrhs_sens) {
+      P.nrhs_sens = r;
+      P.WSS = stride_for(P.WC + r);
+      win_sens = window_doubles(P.WSS, r);
+      layout_sens();
+    }
   }
   if (P.large_state) {
     solve_doubles = even(win_solve);

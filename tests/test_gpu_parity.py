@@ -439,6 +439,32 @@ def test_masked_game_n10():
     assert g.shape == (160, 4) and np.all(np.isfinite(g[:, sol.status == 0]))
 
 
+def test_masked_game_jacobian_consistency():
+    """cfg4 sensitivities in large-state mode (16 right-hand sides per factorisation pass): the full Jacobian must
+    satisfy ∇F_z · (∂z/∂θ) = −∇F_θ (`src/AutoDiff.jl:39`) to backward-error level, and contracting it with z̄ must
+    reproduce the adjoint pullback."""
+    from mcp_b200 import solve_jacobian_θ, solve_pullback
+    game = problems.masked_game(4, 30)
+    mcp = game.mcp
+    Θ = problems.masked_game_thetas(4, 4, seed=7)
+    x0 = problems.masked_game_x0(Θ, 4, 30)
+    sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
+    assert (sol.status == 0).sum() >= 3
+    J = solve_jacobian_θ(mcp, sol, Θ)                                   # n × nθ × B
+    g = solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, 0.5 * sol.s)
+    zbar = np.concatenate([2 * sol.x, 2 * sol.y, 0.5 * sol.s], axis=0)
+    om = OracleMCP(mcp.ir)
+    for b in np.nonzero(sol.status == 0)[0]:
+        gref = J[:, :, b].T @ zbar[:, b]
+        assert np.max(np.abs(g[:, b] - gref)) / max(1.0, np.max(np.abs(gref))) < SENS_TOL
+    b = int(np.nonzero(sol.status == 0)[0][0])
+    Jz = om.JFz(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
+    Jt = om.JFt(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
+    R = Jz @ J[:, :, b] + (Jt.toarray() if hasattr(Jt, "toarray") else Jt)
+    scale = abs(Jz).max() * max(1.0, np.abs(J[:, :, b]).max())
+    assert np.max(np.abs(R)) / scale < 1e-9, np.max(np.abs(R)) / scale
+
+
 def test_lane_change_parity_statistics(lane_game):
     """1 024 random lane-change instances against the C oracle: how often does the GPU follow the oracle's
     trajectory to the bar (same status, Newton steps within ±1, x/y/s within 1e-6 relative)?  Decisions taken
