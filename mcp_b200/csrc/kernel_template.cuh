@@ -1733,7 +1733,11 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
   double* jv = S + SOLVE_OFF_JV;
   double* dinv = S + SOLVE_OFF_DINV;  // D⁻¹, later δs
   double* w = S + SOLVE_OFF_W;        // w, later δy
+#if LARGE_STATE && SOL_IN_SMEM
+  double* sol = V + SOLVE_SOL_SMEM_OFF;   // δx in the permuted ordering: behind the window, in shared memory
+#else
   double* sol = S + SOLVE_OFF_SOL;    // δx in the permuted ordering
+#endif
 #if THETA_IN_SMEM
   double* th = S + SOLVE_OFF_TH;
 #else

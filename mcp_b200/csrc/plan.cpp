@@ -1130,8 +1130,23 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       layout_sens();
     }
   }
+  int sol_in_smem = 0;
   if (P.large_state) {
     solve_doubles = even(win_solve);
+    // δx / the right-hand side is read and written once per pivot step and once per back-substitution step: keep it
+    // in shared memory next to the window when that does not cost an instance (masked game N = 4: 9.6 KB)
+    const int w0 = std::min(ls_cap, warps_for(solve_doubles));
+    if (!P.dense_kernel && w0 >= 1 && std::min(ls_cap, warps_for(solve_doubles + even(N))) >= w0) {
+      sol_in_smem = 1;
+      lay << "#define SOLVE_SOL_SMEM_OFF " << solve_doubles << "\n";
+      solve_doubles += even(N);
+    }
+    if (const char* e = getenv("MCPB200_SOL_SMEM")) {
+      if (!atoi(e) && sol_in_smem) {
+        sol_in_smem = 0;
+        solve_doubles -= even(N);
+      }
+    }
     sens_doubles = even(win_sens);
     P.state_doubles_solve = even(solve_state) + 2;
     P.state_doubles_sens = even(sens_state) + 2;
@@ -1315,7 +1330,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
-  os << "#define NWIDE " << P.nwide << "\n";
+  os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
