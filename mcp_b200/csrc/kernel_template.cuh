@@ -280,7 +280,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   constexpr int PW = (((WC + NPART - 1) / NPART) + 1) & ~1;
   constexpr int WCP = PW * NPART;               // padded matrix width
   constexpr int ES = (WCP + NRHS + 3) & ~1;     // stride of the publish / staging rows (even, one pair of slack)
-  if constexpr (REGWIN && WR <= SUB && PW <= 40) {
+  if constexpr (REGWIN && WR <= SUB && PW <= REGWIN_PW_MAX) {
     // ============ register-resident window ==========================================================
     // Window rows live in REGISTERS for their whole life in the window, each row split over NPART lanes:
     // lane (row, part) holds a[i] = the entry in column j + part·PW + i — a layout relative to the pivot

@@ -1040,12 +1040,15 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (P.dense_schur) P.regwin = 0;   // the rank-1 Schur accumulation works on the shared-memory window
   const int64_t nterms_all = (int64_t)P.t_coef.size();
   const int uts = (P.WC + 1) & ~1;   // UT row stride: even ⇒ 16-byte rows for cp.async.cg
+  // widest register-window part (entries of one window row held by one lane); MCPB200_REGWIN_PW overrides
+  int regwin_pw_max = 40;
+  if (const char* e = getenv("MCPB200_REGWIN_PW")) regwin_pw_max = std::max(2, atoi(e));
   auto window_doubles = [&](int ws, int nrhs) -> int64_t {
     // mirrors the constexpr arithmetic of band_solve (kernel_template.cuh)
     const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
     const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
     const int es = (pw * npart + nrhs + 3) & ~1;
-    const bool regwin = P.regwin && P.R <= P.sub && pw <= 40;
+    const bool regwin = P.regwin && P.R <= P.sub && pw <= regwin_pw_max;
     if (!regwin) return (int64_t)P.R * ws + even(P.R) + 4;                 // + mailbox of the cooperative sweep (NWIDE)
     int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
     w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
@@ -1164,7 +1167,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (!P.dense_kernel && P.sub == 32 && P.ipc_solve >= 1 && P.theta_in_smem) {
     const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
     const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
-    const bool regwin_used = P.regwin && P.R <= P.sub && pw <= 40;
+    const bool regwin_used = P.regwin && P.R <= P.sub && pw <= regwin_pw_max;
     const int np = (P.WC + 1 + 1) / 2, pb = std::min(np, 9), nbatch = (np + pb - 1) / pb;
     if (!regwin_used && !P.dense_schur) {
       P.nwide = std::max(1, std::min({4, 16 / P.ipc_solve, nbatch}));
@@ -1330,7 +1333,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
-  os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n";
+  os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n#define REGWIN_PW_MAX " << regwin_pw_max << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
   os << "#define CVAL_DOUBLES " << cval_doubles << "\n#define SHARED_TABLE_DOUBLES " << shared_table_doubles << "\n";
