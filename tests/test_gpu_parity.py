@@ -493,6 +493,32 @@ def test_lane_change_parity_statistics(lane_game):
     assert ok.mean() >= 0.99
 
 
+def test_masked_game_parity_statistics():
+    """256 masked-game instances (N = 4: all 8 ego masks of 32 scenarios, the data-generation sweep of SURVEY.md §8d)
+    against the C oracle — the path with shape-grouped evaluation, large-state mode and cooperative instances."""
+    from oracle import c_oracle as CO
+    mcp = problems.masked_game(4, 30).mcp
+    B = 256
+    Θ = problems.masked_game_thetas(B, 4, seed=11)
+    x0 = problems.masked_game_x0(Θ, 4, 30)
+    sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
+    ref = CO.solve_batch(mcp.ir, Θ, x0=x0, tol=1e-4)
+    same_status = sol.status == ref.status
+    solved = ref.status == 0
+    ok = same_status.copy()
+    worst = 0.0
+    for b in np.nonzero(solved & same_status)[0]:
+        e = max(rel_err(sol.x[:, b], ref.x[:, b]), rel_err(sol.y[:, b], ref.y[:, b]), rel_err(sol.s[:, b], ref.s[:, b]))
+        steps_ok = abs(int(sol.newton_steps[b]) - int(ref.newton_steps[b])) <= 1
+        ok[b] = steps_ok and e <= RTOL
+        if steps_ok:
+            worst = max(worst, e)
+    print(f"masked-game parity: {ok.sum()}/{B} to the bar, status agreement {same_status.sum()}/{B}, worst rel err {worst:.2e}")
+    assert solved.sum() >= 0.9 * B
+    assert same_status.mean() >= 0.99
+    assert ok.mean() >= 0.98
+
+
 def test_in_library_multi_device_sharding(lane_game):
     """`mcpb200_set_devices`: one host call, θ columns split in contiguous blocks over the GPUs of the box (one
     host thread per device, no collective).  Results must be identical to the single-device run."""
