@@ -1985,43 +1985,70 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 // through the same condensation with D = S Y⁻¹, NRHS_SENS right-hand sides per factorisation pass.
 // ------------------------------------------------------------------------------------------------
 #if HAS_JT
-#ifndef USE_ADJOINT
-#define USE_ADJOINT 1
-#endif
 #ifndef USE_DIRECT_JVP
 #define USE_DIRECT_JVP 1
 #endif
-extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel(const SensParams p) {
+// Per-instance memory layouts of the sensitivity kernels (offsets in doubles, generated by plan.cpp): the forward
+// kernel carries NRHS_SENS right-hand sides per pass; the adjoint kernel needs one, so many more instances fit an SM.
+struct SensLayout {
+  static constexpr bool ADJ = false;
+  static constexpr int NRHS = NRHS_SENS, INST = SENS_INST, WS = WSS;
+  static constexpr long long SMEM = SENS_SMEM_DOUBLES, STATE = SENS_STATE_DOUBLES;
+  static constexpr int OFF_X = SENS_OFF_X, OFF_Y = SENS_OFF_Y, OFF_S = SENS_OFF_S, OFF_JV = SENS_OFF_JV, OFF_JTV = SENS_OFF_JTV,
+                       OFF_DINV = SENS_OFF_DINV, OFF_WQ = SENS_OFF_WQ, OFF_SOL = SENS_OFF_SOL, OFF_STAGE = SENS_OFF_STAGE,
+                       OFF_WIN = SENS_OFF_WIN;
+#if THETA_IN_SMEM
+  static constexpr int OFF_TH = SENS_OFF_TH;
+#endif
+};
+#if HAS_ADJOINT
+struct AdjLayout {
+  static constexpr bool ADJ = true;
+  static constexpr int NRHS = 1, INST = ADJ_INST, WS = WS1;
+  static constexpr long long SMEM = ADJ_SMEM_DOUBLES, STATE = ADJ_STATE_DOUBLES;
+  static constexpr int OFF_X = ADJ_OFF_X, OFF_Y = ADJ_OFF_Y, OFF_S = ADJ_OFF_S, OFF_JV = ADJ_OFF_JV, OFF_JTV = ADJ_OFF_JTV,
+                       OFF_DINV = ADJ_OFF_DINV, OFF_WQ = ADJ_OFF_WQ, OFF_SOL = ADJ_OFF_SOL, OFF_STAGE = ADJ_OFF_STAGE,
+                       OFF_WIN = ADJ_OFF_WIN;
+#if THETA_IN_SMEM
+  static constexpr int OFF_TH = ADJ_OFF_TH;
+#endif
+};
+#endif
+
+template <class L>
+__device__ __forceinline__ void sens_body(const SensParams& p) {
   extern __shared__ double smem[];
   const int sl = threadIdx.x % SUB;
   const int slot = threadIdx.x / SUB;
   const unsigned smask = sub_mask(threadIdx.x & 31);
-  // Pullback only (z̄ → θ̄): adjoint mode — ONE solve with Cᵀ per instance instead of one solve of C per column of
-  // ∇F_θ (nθ = 160 for the masked game at N = 10).  The Jacobian and the pushforward keep the forward solves.
-  const bool adjoint = HAS_ADJOINT && USE_ADJOINT && p.zbar && p.thetabar && !p.dzdtheta && !p.z_p;
+  // Pullback only (z̄ → θ̄) runs in mcp_adj_kernel: adjoint mode — ONE solve with Cᵀ per instance instead of one solve
+  // of C per column of ∇F_θ (nθ = 160 for the masked game at N = 10).  The Jacobian and the pushforward keep the
+  // forward solves (mcp_sens_kernel).
+  constexpr bool adjoint = L::ADJ;
+  constexpr int NRHS_L = L::NRHS;
   load_shared_tables(smem, adjoint);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
-  double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SENS_SMEM_DOUBLES;
+  double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * L::SMEM;
 #if LARGE_STATE
-  double* S = p.state + ((size_t)blockIdx.x * SENS_INST + slot) * SENS_STATE_DOUBLES;
+  double* S = p.state + ((size_t)blockIdx.x * L::INST + slot) * L::STATE;
   double* W = V;
 #else
   double* S = V;
-  double* W = V + SENS_OFF_WIN;
+  double* W = V + L::OFF_WIN;
 #endif
-  double* x = S + SENS_OFF_X;
-  double* y = S + SENS_OFF_Y;
-  double* s = S + SENS_OFF_S;
-  double* jv = S + SENS_OFF_JV;
-  double* jtv = S + SENS_OFF_JTV;
-  double* dinv = S + SENS_OFF_DINV;
-  double* wq = S + SENS_OFF_WQ;    // [NRHS_SENS][NY]
-  double* sol = S + SENS_OFF_SOL;  // [NRHS_SENS][NRED]
+  double* x = S + L::OFF_X;
+  double* y = S + L::OFF_Y;
+  double* s = S + L::OFF_S;
+  double* jv = S + L::OFF_JV;
+  double* jtv = S + L::OFF_JTV;
+  double* dinv = S + L::OFF_DINV;
+  double* wq = S + L::OFF_WQ;    // [NRHS_L][NY]
+  double* sol = S + L::OFF_SOL;  // [NRHS_L][NRED]
 #if THETA_IN_SMEM
-  double* th = S + SENS_OFF_TH;
+  double* th = S + L::OFF_TH;
 #endif
-  double* Cval = p.scratch + ((size_t)blockIdx.x * SENS_INST + slot) * SENS_SCRATCH;
+  double* Cval = p.scratch + ((size_t)blockIdx.x * L::INST + slot) * SENS_SCRATCH;
   double* UT = Cval + CVAL_DOUBLES;
   constexpr int NZ = NX + 2 * NY;
 
@@ -2048,8 +2075,8 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
       for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = 0.0;
     __syncwarp(smask);
     int bad = 0;
-#if HAS_ADJOINT && USE_ADJOINT
-    if (adjoint) {
+#if HAS_ADJOINT
+    if constexpr (adjoint) {
       // Jᵀλ = z̄ condensed like the forward system:  Cᵀ λ₁ = x̄ − H_xᵀ v,  v = D⁻¹ȳ − s̄,
       // λ₂ = v − D⁻¹ G_yᵀ λ₁,  θ̄ = −∇F_θᵀ [λ₁; λ₂]   (the complementarity rows do not depend on θ)
       const double* zb = p.zbar + inst * NZ;
@@ -2063,7 +2090,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
       __syncwarp(smask);
       assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
       __syncwarp(smask);
-      bad = band_solve<1, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask, 0, DT_SRC);
+      bad = band_solve<1, L::WS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + L::OFF_STAGE, sl, smask, 0, DT_SRC);
       if (!bad) {
         for (int i = sl; i < NRED; i += SUB) {
           const double li = sol[i];
@@ -2089,11 +2116,11 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
 #if USE_DIRECT_JVP
     if (p.z_p && !p.dzdtheta && !p.zbar) {
       // Pushforward only (θ_p → z_p, the Dual overload): the tangents are the right-hand sides — r = −∇F_θ θ_p, one
-      // solve of C per tangent (NRHS_SENS at a time) instead of one per column of ∇F_θ followed by a contraction
-      for (int p0 = 0; p0 < p.P; p0 += NRHS_SENS) {
-        const int np = min(NRHS_SENS, p.P - p0);
-        for (int i = sl; i < NRHS_SENS * NY; i += SUB) wq[i] = 0.0;
-        for (int i = sl; i < NRHS_SENS * NRED; i += SUB) sol[i] = 0.0;
+      // solve of C per tangent (NRHS_L at a time) instead of one per column of ∇F_θ followed by a contraction
+      for (int p0 = 0; p0 < p.P; p0 += NRHS_L) {
+        const int np = min(NRHS_L, p.P - p0);
+        for (int i = sl; i < NRHS_L * NY; i += SUB) wq[i] = 0.0;
+        for (int i = sl; i < NRHS_L * NRED; i += SUB) sol[i] = 0.0;
         assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
         __syncwarp(smask);
         for (int q = 0; q < NT; ++q) {
@@ -2115,7 +2142,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
             sol[rp * NRED + i] = r;
           }
         __syncwarp(smask);
-        if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask)) {
+        if (band_solve<NRHS_L, L::WS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + L::OFF_STAGE, sl, smask)) {
           bad = 1;
           break;
         }
@@ -2138,10 +2165,10 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
       continue;
     }
 #endif
-    for (int q0 = 0; q0 < NT; q0 += NRHS_SENS) {
-      const int nq = min(NRHS_SENS, NT - q0);
-      for (int i = sl; i < NRHS_SENS * NY; i += SUB) wq[i] = 0.0;
-      for (int i = sl; i < NRHS_SENS * NRED; i += SUB) sol[i] = 0.0;
+    for (int q0 = 0; q0 < NT; q0 += NRHS_L) {
+      const int nq = min(NRHS_L, NT - q0);
+      for (int i = sl; i < NRHS_L * NY; i += SUB) wq[i] = 0.0;
+      for (int i = sl; i < NRHS_L * NRED; i += SUB) sol[i] = 0.0;
       assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
       __syncwarp(smask);
       // right-hand sides r = −∇F_θ[:, q]:  G rows go to the reduced rhs, H rows to w = D⁻¹ r₂
@@ -2164,7 +2191,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
         }
       }
       __syncwarp(smask);
-      if (band_solve<NRHS_SENS, WSS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SENS_OFF_STAGE, sl, smask)) {
+      if (band_solve<NRHS_L, L::WS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + L::OFF_STAGE, sl, smask)) {
         bad = 1;
         break;
       }
@@ -2210,4 +2237,9 @@ extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel
     __syncwarp(smask);
   }
 }
+
+extern "C" __global__ void __launch_bounds__(SUB * SENS_INST, 1) mcp_sens_kernel(const SensParams p) { sens_body<SensLayout>(p); }
+#if HAS_ADJOINT
+extern "C" __global__ void __launch_bounds__(SUB * ADJ_INST, 1) mcp_adj_kernel(const SensParams p) { sens_body<AdjLayout>(p); }
+#endif
 #endif  // HAS_JT

@@ -132,7 +132,7 @@ struct DevBuf {
 struct DeviceState {
   int dev = -1;
   CUmodule mod = nullptr;
-  CUfunction f_solve = nullptr, f_sens = nullptr;
+  CUfunction f_solve = nullptr, f_sens = nullptr, f_adj = nullptr;
   int num_sms = 0, regs_solve = 0, regs_sens = 0;
   DevBuf scratch, state, counters, deferred, steps_tmp;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_d2h1 = nullptr;
@@ -340,7 +340,8 @@ int compile_source(mcpb200_problem* h, uint32_t flags) {
     const Plan& P = h->plan;
     // (dense kernels v1/v2 are compiled for two CTAs per SM: __launch_bounds__(256, 2))
     const int dense_resident = P.dense_threads * ((P.dense_kernel == 1 || P.dense_kernel == 2) ? 2 : 1);
-    const int threads = std::max({P.dense_kernel ? dense_resident : P.sub * P.ipc_solve * P.nwide, P.has_jt ? P.sub * P.ipc_sens : 0, 32});
+    const int threads = std::max({P.dense_kernel ? dense_resident : P.sub * P.ipc_solve * P.nwide, P.has_jt ? P.sub * P.ipc_sens : 0,
+                                  P.has_adjoint ? P.sub * P.ipc_adj : 0, 32});
     const int maxreg = std::min(255, (65536 / threads) / 8 * 8);
     auto worker = [&] {
       for (;;) {
@@ -413,6 +414,10 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
       CU_TRY(h, D.ModuleGetFunction(&st->f_sens, st->mod, "mcp_sens_kernel"));
       CU_TRY(h, D.FuncSetAttribute(st->f_sens, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_sens));
       D.FuncGetAttribute(&st->regs_sens, CU_FUNC_ATTRIBUTE_NUM_REGS, st->f_sens);
+      if (h->plan.has_adjoint) {
+        CU_TRY(h, D.ModuleGetFunction(&st->f_adj, st->mod, "mcp_adj_kernel"));
+        CU_TRY(h, D.FuncSetAttribute(st->f_adj, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_adj));
+      }
     }
     CUDA_TRY(h, cudaEventCreate(&st->ev0));
     CUDA_TRY(h, cudaEventCreate(&st->ev1));
@@ -435,14 +440,15 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
   const unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve * P.nwide);
   const size_t scratch_bytes = (size_t)st->num_sms * P.ipc_solve * P.scratch_doubles_solve * 8;
-  if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * P.ipc_sens * P.scratch_doubles_sens * 8)))
+  if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * std::max(P.ipc_sens, P.ipc_adj) * P.scratch_doubles_sens * 8)))
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
   p.state = nullptr;
   if (P.large_state) {
-    if (st->state.ensure((size_t)st->num_sms * std::max((size_t)P.ipc_solve * P.state_doubles_solve,
-                                                        (size_t)P.ipc_sens * P.state_doubles_sens) * 8 + 64))
+    if (st->state.ensure((size_t)st->num_sms * std::max({(size_t)P.ipc_solve * P.state_doubles_solve,
+                                                         (size_t)P.ipc_sens * P.state_doubles_sens,
+                                                         (size_t)P.ipc_adj * P.state_doubles_adj}) * 8 + 64))
       return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(state) failed");
     p.state = (double*)st->state.p;
   }
@@ -481,17 +487,21 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
 
 int launch_sens(mcpb200_problem* h, DeviceState* st, SensParams& p, cudaStream_t stream) {
   const Plan& P = h->plan;
-  const long long ctas_needed = (p.B + P.ipc_sens - 1) / P.ipc_sens;
+  // pullback only → the adjoint kernel (one transposed solve per instance, its own denser layout)
+  const bool adj = P.has_adjoint && st->f_adj && p.zbar && p.thetabar && !p.dzdtheta && !p.z_p;
+  const int ipc = adj ? P.ipc_adj : P.ipc_sens;
+  const long long ctas_needed = (p.B + ipc - 1) / ipc;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(st->num_sms, ctas_needed));
-  const size_t scratch_bytes = (size_t)st->num_sms * std::max((size_t)P.ipc_sens * P.scratch_doubles_sens,
+  const size_t scratch_bytes = (size_t)st->num_sms * std::max((size_t)std::max(P.ipc_sens, P.ipc_adj) * P.scratch_doubles_sens,
                                                               (size_t)P.ipc_solve * P.scratch_doubles_solve) * 8;
   if (st->scratch.ensure(scratch_bytes)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
   p.state = nullptr;
   if (P.large_state) {
-    if (st->state.ensure((size_t)st->num_sms * std::max((size_t)P.ipc_solve * P.state_doubles_solve,
-                                                        (size_t)P.ipc_sens * P.state_doubles_sens) * 8 + 64))
+    if (st->state.ensure((size_t)st->num_sms * std::max({(size_t)P.ipc_solve * P.state_doubles_solve,
+                                                         (size_t)P.ipc_sens * P.state_doubles_sens,
+                                                         (size_t)P.ipc_adj * P.state_doubles_adj}) * 8 + 64))
       return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(state) failed");
     p.state = (double*)st->state.p;
   }
@@ -499,7 +509,8 @@ int launch_sens(mcpb200_problem* h, DeviceState* st, SensParams& p, cudaStream_t
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
-  CU_TRY(h, driver().LaunchKernel(st->f_sens, grid, 1, 1, (unsigned)(P.sub * P.ipc_sens), 1, 1, (unsigned)P.smem_sens, (CUstream)stream, args, nullptr));
+  CU_TRY(h, driver().LaunchKernel(adj ? st->f_adj : st->f_sens, grid, 1, 1, (unsigned)(P.sub * ipc), 1, 1,
+                                  (unsigned)(adj ? P.smem_adj : P.smem_sens), (CUstream)stream, args, nullptr));
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
   st->timed = true;
   st->pending = true;

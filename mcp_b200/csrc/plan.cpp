@@ -1186,6 +1186,35 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     P.ipc_sens = 1;
   }
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
+  // Adjoint-mode pullback (kernel_template.cuh, mcp_adj_kernel): the forward layout with ONE right-hand side, so
+  // far more instances fit an SM than in the forward kernel (lane-change: 4 → 14).  MCPB200_ADJOINT=0 disables it.
+  P.has_adjoint = (P.has_jt && !P.dense_schur && !P.dense_kernel && P.kl == P.ku) ? 1 : 0;
+  if (const char* e = getenv("MCPB200_ADJOINT")) P.has_adjoint = P.has_adjoint && atoi(e) != 0;
+  int64_t adj_doubles = 0;
+  if (P.has_adjoint) {
+    off = 0;
+    place("ADJ_OFF_X", nx);
+    place("ADJ_OFF_Y", ny);
+    place("ADJ_OFF_S", ny);
+    place("ADJ_OFF_JV", njv);
+    place("ADJ_OFF_JTV", njtv);
+    place("ADJ_OFF_DINV", ny);
+    place("ADJ_OFF_WQ", ny);
+    place("ADJ_OFF_SOL", N);
+    if (P.theta_in_smem) place("ADJ_OFF_TH", nt);
+    place("ADJ_OFF_STAGE", 0);
+    const int64_t adj_state = off;
+    place("ADJ_OFF_WIN", win_solve);
+    adj_doubles = off;
+    if (P.large_state) {
+      adj_doubles = even(win_solve);
+      P.state_doubles_adj = even(adj_state) + 2;
+    }
+    P.ipc_adj = warps_for(adj_doubles);
+    if (P.large_state) P.ipc_adj = std::min(P.ipc_adj, ls_cap);
+    if (P.ipc_adj < 1) P.has_adjoint = 0;
+    P.smem_adj = (shared_table_doubles + adj_doubles * std::max(P.ipc_adj, 1)) * 8;
+  }
   if (P.dense_kernel) {
     const int dtr = (N + 15) / 16, dnp = 16 * dtr;
     off = 0;
@@ -1351,8 +1380,10 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     emit_table(os, "double", "D_BASE", P.d_base, true);
     // Adjoint sensitivities (θ̄ from z̄ with ONE solve of Cᵀ instead of nθ solves of C): the same non-zeros in
     // column-major order — first dest of each column, window position of its row, index into Cval.
-    const bool adjoint = P.has_jt && !P.dense_schur && !P.dense_kernel && P.kl == P.ku;
+    const bool adjoint = P.has_adjoint != 0;
     os << "#define HAS_ADJOINT " << (adjoint ? 1 : 0) << "\n";
+    os << "#define ADJ_INST " << P.ipc_adj << "\n#define ADJ_SMEM_DOUBLES " << adj_doubles << "\n#define ADJ_STATE_DOUBLES "
+       << P.state_doubles_adj << "\n";
     if (adjoint) {
       std::vector<int32_t> ord(P.d_row.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int32_t)i;

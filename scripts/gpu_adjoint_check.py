@@ -7,7 +7,7 @@ from mcp_b200.solver import _handle
 def both(make, Θ, x0=None, tol=1e-6):
     out = {}
     for mode in ("1", "0"):
-        os.environ["MCPB200_DEFS"] = "USE_ADJOINT=" + mode
+        os.environ["MCPB200_ADJOINT"] = mode
         mcp = make()
         sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=tol)
         g = solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, 0.5 * sol.s)

@@ -136,12 +136,12 @@ def test_sensitivities_lane_change(lane_game):
 
 def test_adjoint_pullback_matches_forward(monkeypatch):
     """The pullback runs in adjoint mode (one solve with Cᵀ per instance); the forward mode (one solve of C per column
-    of ∇F_θ, the structure of `src/AutoDiff.jl:18-40,59-76`) is kept behind a build switch.  Both must give the same
+    of ∇F_θ, the structure of `src/AutoDiff.jl:18-40,59-76`) is kept behind a switch (MCPB200_ADJOINT=0).  Both must give the same
     θ̄ — on the masked game (nθ = 40: 40 factorisations vs 1) and on the lane-change game."""
     from mcp_b200 import solve_pullback
 
     def pull(make, Θ, x0, tol, mode):
-        monkeypatch.setenv("MCPB200_DEFS", "USE_ADJOINT=" + mode)
+        monkeypatch.setenv("MCPB200_ADJOINT", mode)
         mcp = make()
         sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=tol)
         return sol, solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, 0.5 * sol.s)
