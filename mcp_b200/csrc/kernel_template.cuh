@@ -1694,6 +1694,202 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
   }
 }
 #endif  // DENSE_KERNEL == 2
+#elif TINY_KERNEL
+// ------------------------------------------------------------------------------------------------
+// Thread-per-instance solve kernel for problems of a few unknowns (NRED ≤ 6, NY ≤ 8: the README QP).  The iterate,
+// the condensed matrix and every intermediate live in registers; residual, Jacobian entries, assembly, right-hand
+// side and H_x products are straight-line code generated from the plan's tables (tiny_* functions); the
+// factorisation is a fully unrolled dense LU with partial pivoting.  The loop is the same literal restatement of
+// src/solver.jl:63-121 as in the other kernels; the two-pass budget parks long runs exactly like there (one slow
+// thread would otherwise hold its warp).
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(128) mcp_solve_kernel(const SolveParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_work = p.pass ? (long long)p.counters[3] : p.B;
+  const bool valid = idx < n_work;
+  int my_steps = 0, my_solved = 0;
+  if (valid) {
+    const long long inst = p.pass ? (long long)p.deferred[idx] : idx;
+    double th[NT > 0 ? NT : 1], x[NX], y[NY], s[NY];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) th[i] = p.theta[inst * NT + i];
+    double eps = 1.0;                                        // :67
+    double kkt = __longlong_as_double(0x7ff0000000000000LL);  // :68
+    int status = 0, outer = 1, steps = 0;                    // :69-70
+    if (p.pass) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = p.x_out[inst * NX + i];
+#pragma unroll
+      for (int i = 0; i < NY; ++i) {
+        y[i] = p.y_out[inst * NY + i];
+        s[i] = p.s_out[inst * NY + i];
+      }
+      eps = p.eps_out[inst];
+      kkt = p.kkt_out[inst];
+      outer = p.outer_out[inst];
+      steps = p.steps_out[inst];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NY; ++i) {
+        y[i] = p.y0 ? p.y0[inst * NY + i] : 1.0;
+        s[i] = p.s0 ? p.s0[inst * NY + i] : 1.0;
+      }
+    }
+    const double tol = p.tol;
+    bool parked = false;
+    while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
+      if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
+        parked = true;
+        break;
+      }
+      int inner = 1;  // :72
+      status = 0;     // :73
+      while (kkt > eps && inner < p.max_inner) {  // :75
+        double g[NX], h[NY], jv[NJV > 0 ? NJV : 1], dinv[NY], w[NY], C[NRED][NRED + 1];
+        tiny_eval(x, y, th, g, h, jv);  // :79-80
+        double fmax_ = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) fmax_ = nanmax(fmax_, fabs(g[i]));
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+          const double f2 = h[k] - s[k];
+          const double f3 = s[k] * y[k] - eps;
+          const double yt = y[k] + tol;
+          const double di = 1.0 / (tol + s[k] / yt);
+          dinv[k] = di;
+          w[k] = di * (-f2 - f3 / yt);
+          fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
+        }
+        const double kkt_new = fmax_;  // :107
+        tiny_assemble(jv, th, dinv, tol, C);
+        tiny_rhs(g, jv, th, w, C);
+        // ---- dense LU with partial pivoting, rows swapped in registers; forward substitution in column NRED ----------
+        bool failed = false;
+        double rpv[NRED];
+#pragma unroll
+        for (int j = 0; j < NRED; ++j) {
+          int pr = j;
+          unsigned best = (unsigned)__double2hiint(fabs(C[j][j])) & 0xffffff00u;
+#pragma unroll
+          for (int i = j + 1; i < NRED; ++i) {
+            const unsigned k = (unsigned)__double2hiint(fabs(C[i][j])) & 0xffffff00u;
+            if (k > best) {
+              best = k;
+              pr = i;
+            }
+          }
+#pragma unroll
+          for (int i = j + 1; i < NRED; ++i)
+            if (pr == i) {
+#pragma unroll
+              for (int c = j; c <= NRED; ++c) {
+                const double t = C[i][c];
+                C[i][c] = C[j][c];
+                C[j][c] = t;
+              }
+            }
+          const double piv = C[j][j];
+          if (!(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) failed = true;  // :84-88
+          const double rp = 1.0 / piv;
+          rpv[j] = rp;
+#pragma unroll
+          for (int i = j + 1; i < NRED; ++i) {
+            const double m = -(C[i][j] * rp);
+#pragma unroll
+            for (int c = j + 1; c <= NRED; ++c) C[i][c] = fma(m, C[j][c], C[i][c]);
+          }
+        }
+        double a_s = 1.0, a_y = 1.0;
+        double sol[NRED], ds[NY], dy[NY];
+        if (!failed) {
+#pragma unroll
+          for (int j = NRED - 1; j >= 0; --j) {
+            const double xj = C[j][NRED] * rpv[j];
+            sol[j] = xj;
+#pragma unroll
+            for (int i = 0; i < j; ++i) C[i][NRED] = fma(-C[i][j], xj, C[i][NRED]);
+          }
+          // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
+          double hx[NY];
+          tiny_hx(jv, th, sol, hx);
+#pragma unroll
+          for (int k = 0; k < NY; ++k) {
+            dy[k] = w[k] - dinv[k] * hx[k];
+            const double f3 = s[k] * y[k] - eps;
+            ds[k] = -(f3 + s[k] * dy[k]) / (y[k] + tol);
+          }
+          // `fraction_to_the_boundary_linesearch` (src/solver.jl:127-138), once for (s, δs), once for (y, δy)
+          const double c995 = 1.0 - 0.995;
+#pragma unroll 1
+          for (int which = 0; which < 2; ++which) {
+            double alpha = 1.0;
+            bool ok = false;
+            for (int it = 0; it < 1200; ++it) {
+              bool viol = false;
+#pragma unroll
+              for (int k = 0; k < NY; ++k) {
+                const double v = which ? y[k] : s[k], d = which ? dy[k] : ds[k];
+                viol = viol || (v + alpha * d < c995 * v);  // :129
+              }
+              if (!viol) {
+                ok = true;
+                break;
+              }
+              if (alpha < p.min_stepsize) break;  // :130
+              alpha *= 0.5;                       // :134
+            }
+            if (!ok) alpha = __longlong_as_double(0x7ff8000000000000LL);
+            if (which) a_y = alpha; else a_s = alpha;
+          }
+          failed = (a_s != a_s) || (a_y != a_y);  // :96-100
+        }
+        if (failed) {
+          status = 1;
+          break;
+        }
+        tiny_update_x(x, sol, a_s);  // :103
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+          s[k] += a_s * ds[k];  // :104
+          y[k] += a_y * dy[k];  // :105
+        }
+        kkt = kkt_new;  // :107
+        ++inner;        // :108
+        ++steps;
+      }
+      eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);  // :111-113
+      ++outer;                                                                                              // :114
+    }
+    if (!parked && outer == p.max_outer) status = 1;  // :117-119
+#pragma unroll
+    for (int i = 0; i < NX; ++i) p.x_out[inst * NX + i] = x[i];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      p.y_out[inst * NY + i] = y[i];
+      p.s_out[inst * NY + i] = s[i];
+    }
+    p.kkt_out[inst] = kkt;
+    p.eps_out[inst] = eps;
+    p.outer_out[inst] = outer;
+    p.status_out[inst] = status;
+    p.steps_out[inst] = steps;
+    if (parked) {
+      p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+    } else {
+      my_steps = steps;
+      my_solved = (status == 0);
+    }
+  }
+  // warp-aggregated statistics (every lane of the warp arrives here)
+  __syncwarp();
+  const int ws = __reduce_add_sync(FULLMASK, my_steps), wv = __reduce_add_sync(FULLMASK, my_solved);
+  if ((threadIdx.x & 31) == 0) {
+    if (ws) atomicAdd(p.counters + 1, (unsigned long long)ws);
+    if (wv) atomicAdd(p.counters + 2, (unsigned long long)wv);
+  }
+}
 #else   // !DENSE_KERNEL
 // ------------------------------------------------------------------------------------------------
 // The solve kernel: persistent CTAs; every sub-warp (SUB lanes) pulls instances from a global queue and

@@ -406,7 +406,8 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
     st->num_sms = prop.multiProcessorCount;
     CU_TRY(h, D.ModuleLoadData(&st->mod, h->cubin.data()));
     CU_TRY(h, D.ModuleGetFunction(&st->f_solve, st->mod, "mcp_solve_kernel"));
-    CU_TRY(h, D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_solve));
+    if (!h->plan.tiny_kernel)
+      CU_TRY(h, D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_solve));
     if (const char* e = getenv("MCPB200_CARVEOUT"))   // tuning: shared-memory carve-out in percent (the rest of the 256 KB is L1)
       D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, atoi(e));
     D.FuncGetAttribute(&st->regs_solve, CU_FUNC_ATTRIBUTE_NUM_REGS, st->f_solve);
@@ -437,8 +438,14 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   const Plan& P = h->plan;
   const long long ctas_needed = (p.B + P.ipc_solve - 1) / P.ipc_solve;
   const long long max_ctas = (long long)st->num_sms * (P.dense_kernel ? P.dense_ctas_per_sm : 1);
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
-  const unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve * P.nwide);
+  unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas_needed));
+  unsigned block = P.dense_kernel ? (unsigned)P.dense_threads : (unsigned)(P.sub * P.ipc_solve * P.nwide);
+  unsigned smem_bytes = (unsigned)P.smem_solve;
+  if (P.tiny_kernel) {   // one thread per instance, no shared memory, not persistent
+    block = 128;
+    grid = (unsigned)std::max<long long>(1, (p.B + block - 1) / block);
+    smem_bytes = 0;
+  }
   const size_t scratch_bytes = (size_t)st->num_sms * P.ipc_solve * P.scratch_doubles_solve * 8;
   if (st->scratch.ensure(std::max(scratch_bytes, (size_t)st->num_sms * std::max(P.ipc_sens, P.ipc_adj) * P.scratch_doubles_sens * 8)))
     return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(scratch) failed");
@@ -470,13 +477,13 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
   p.pass = 0;
-  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+  CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr));
   st->launches = 1;
   st->two_pass = budget > 0;
   if (budget > 0) {
     CUDA_TRY(h, cudaEventRecord(st->ev_mid, stream));
     p.pass = 1;
-    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, (unsigned)P.smem_solve, (CUstream)stream, args, nullptr));
+    CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr));
     st->launches = 2;
   }
   CUDA_TRY(h, cudaEventRecord(st->ev1, stream));
@@ -624,7 +631,7 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->n_jac_constant = P.n_const_entries;
   info->n_assembly_dests = (int)P.d_row.size();
   info->n_assembly_terms = (int)P.t_coef.size();
-  info->threads_per_instance = P.dense_kernel ? P.dense_threads : P.sub * P.nwide;
+  info->threads_per_instance = P.tiny_kernel ? 1 : (P.dense_kernel ? P.dense_threads : P.sub * P.nwide);
   info->instances_per_cta = P.ipc_solve;
   info->ctas_per_sm = P.dense_kernel ? P.dense_ctas_per_sm : 1;
   info->smem_bytes_per_cta = (int)P.smem_solve;

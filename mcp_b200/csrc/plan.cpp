@@ -905,6 +905,10 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
         v.erase(std::remove_if(v.begin(), v.end(), [](const Term& t) { return t.k >= 0; }), v.end());
       }
   }
+  // Problems of a few unknowns (the README QP: nx = ny = 2): one THREAD per instance, everything in registers, all
+  // tables turned into straight-line code (kernel_template.cuh, TINY_KERNEL).  MCPB200_TINY=0 disables it.
+  P.tiny_kernel = (!P.dense_kernel && !P.dense_schur && N <= 6 && ny <= 8 && nt <= 32 && P.op.size() <= 4000) ? 1 : 0;
+  if (const char* e = getenv("MCPB200_TINY")) P.tiny_kernel = P.tiny_kernel && atoi(e) != 0;
   P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
   if (P.has_jt) {
     // right-hand sides per factorisation pass: as many (≤ 16) as keep one instance within shared memory
@@ -1362,6 +1366,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
+  os << "#define TINY_KERNEL " << P.tiny_kernel << "\n";
   os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n#define REGWIN_PW_MAX " << regwin_pw_max << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";
@@ -1485,6 +1490,63 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                                    "double* __restrict__ jv, double* __restrict__ jtv",
                    "x, y, th, jv, jtv", outs, {"jv", "jtv"}, P.sub, &P.units, unit_prelude, use_shapes);
     }
+  }
+  if (P.tiny_kernel) {
+    auto val = [&](int code) -> std::string {
+      if (code == -1) return "1.0";
+      if (code >= 0) return "jv[" + std::to_string(code) + "]";
+      return "th[" + std::to_string(-2 - code) + "]";
+    };
+    const std::string A_X = "const double (&x)[NX]", A_Y = "const double (&y)[NY]", A_TH = "const double (&th)[NT > 0 ? NT : 1]",
+                      A_JV = "const double (&jv)[NJV > 0 ? NJV : 1]";
+    os << "// ---- thread-per-instance kernel: the tables above as straight-line code on register arrays ----\n";
+    os << "__device__ __forceinline__ void tiny_eval(" << A_X << ", " << A_Y << ", " << A_TH
+       << ", double (&g)[NX], double (&h)[NY], double (&jv)[NJV > 0 ? NJV : 1]) {\n";
+    {
+      std::vector<int32_t> roots;
+      for (int i = 0; i < nx + ny; ++i) roots.push_back(P.gh_nodes[i]);
+      for (int i = 0; i < njv; ++i) roots.push_back(P.jv_nodes[i]);
+      E.body(os, roots);
+      for (int i = 0; i < nx; ++i) os << "  g[" << i << "] = " << E.operand(P.gh_nodes[i]) << ";\n";
+      for (int i = 0; i < ny; ++i) os << "  h[" << i << "] = " << E.operand(P.gh_nodes[nx + i]) << ";\n";
+      for (int i = 0; i < njv; ++i) os << "  jv[" << i << "] = " << E.operand(P.jv_nodes[i]) << ";\n";
+    }
+    os << "}\n";
+    // C (new ordering) with the right-hand side in column NRED
+    os << "__device__ __forceinline__ void tiny_assemble(" << A_JV << ", " << A_TH
+       << ", const double (&dinv)[NY], const double tol, double (&C)[NRED][NRED + 1]) {\n";
+    os << "#pragma unroll\n  for (int i = 0; i < NRED; ++i)\n#pragma unroll\n    for (int j = 0; j < NRED; ++j) C[i][j] = 0.0;\n";
+    for (size_t d = 0; d < P.d_row.size(); ++d) {
+      os << "  C[" << P.d_row[d] << "][" << P.d_col[d] << "] = " << dlit(P.d_base[d]);
+      if (P.d_diag[d]) os << " + tol";
+      for (int t = P.d_tptr[d]; t < P.d_tptr[d + 1]; ++t) {
+        os << " + " << dlit(P.t_coef[t]) << " * " << val(P.t_a[t]);
+        if (P.t_k[t] >= 0) os << " * dinv[" << P.t_k[t] << "] * " << val(P.t_b[t]);
+      }
+      os << ";\n";
+    }
+    os << "}\n";
+    os << "__device__ __forceinline__ void tiny_rhs(const double (&g)[NX], " << A_JV << ", " << A_TH
+       << ", const double (&w)[NY], double (&C)[NRED][NRED + 1]) {\n";
+    for (int i = 0; i < N; ++i) {
+      os << "  C[" << i << "][NRED] = -g[" << P.r_grow[i] << "]";
+      for (int e = P.r_ptr[i]; e < P.r_ptr[i + 1]; ++e)
+        os << " - " << dlit(P.r_coef[e]) << " * " << val(P.r_code[e]) << " * w[" << P.r_k[e] << "]";
+      os << ";\n";
+    }
+    os << "}\n";
+    os << "__device__ __forceinline__ void tiny_hx(" << A_JV << ", " << A_TH
+       << ", const double (&v)[NRED], double (&hx)[NY]) {\n";
+    for (int k = 0; k < ny; ++k) {
+      os << "  hx[" << k << "] = 0.0";
+      for (int e = P.h_ptr[k]; e < P.h_ptr[k + 1]; ++e)
+        os << " + " << dlit(P.h_coef[e]) << " * " << val(P.h_code[e]) << " * v[" << P.h_col[e] << "]";
+      os << ";\n";
+    }
+    os << "}\n";
+    os << "__device__ __forceinline__ void tiny_update_x(double (&x)[NX], const double (&v)[NRED], const double a) {\n";
+    for (int c = 0; c < N; ++c) os << "  x[" << P.perm[c] << "] += a * v[" << c << "];\n";
+    os << "}\n";
   }
   os << kernel_template;
   P.source = os.str();

@@ -68,6 +68,7 @@ struct Plan {
   int large_state = 0;                // per-instance vectors in a global block, only the window in shared memory
   int64_t state_doubles_solve = 0, state_doubles_sens = 0;
   int dense_schur = 0;
+  int tiny_kernel = 0;                // thread-per-instance solve kernel for problems of a few unknowns (README QP)
   int dense_kernel = 0;               // CTA-per-instance dense solve kernel (kernel_template.cuh, DENSE_KERNEL)
   int dense_ctas_per_sm = 1;
   int dense_threads = 256;            // CTA size of the dense kernel (v3: 512)

@@ -147,9 +147,16 @@ def test_plan_variants_are_selected_and_compile(monkeypatch, tmp_path):
     m = _macros(capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY).source())
     assert (m["REGWIN"], m["SUB"], m["DENSE_KERNEL"], m["LARGE_STATE"]) == ("1", "32", "0", "0")
     assert int(m["KL"]) <= 12 and int(m["WR"]) <= 13          # annealed ordering (RCM alone gives 17)
-    # tiny QP: two instances per warp
-    m = _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())
-    assert (m["SUB"], m["DENSE_KERNEL"]) == ("16", "0")
+    # tiny QP: one THREAD per instance for the solve (straight-line generated code on register arrays); the
+    # sensitivity kernels keep two instances per warp
+    h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    m = _macros(h.source())
+    assert (m["TINY_KERNEL"], m["SUB"], m["DENSE_KERNEL"]) == ("1", "16", "0") and h.info()["threads_per_instance"] == 1
+    assert "tiny_assemble" in h.source() and "C[0][0] = " in h.source()
+    monkeypatch.setenv("MCPB200_TINY", "0")
+    h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["TINY_KERNEL"] == "0" and h.info()["threads_per_instance"] == 16
+    monkeypatch.delenv("MCPB200_TINY")
     # dense QP with G_y = −H_xᵀ and an affine residual: CTA-per-instance kernel, matrix in register tiles (v3)
     h = capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY)
     m = _macros(h.source())
