@@ -2211,6 +2211,7 @@ struct AdjLayout {
 };
 #endif
 
+#define SENS_NAN __longlong_as_double(0x7ff8000000000000LL)
 template <class L>
 __device__ __forceinline__ void sens_body(const SensParams& p) {
   extern __shared__ double smem[];
@@ -2303,6 +2304,10 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
           }
           p.thetabar[inst * NT + q] = acc;
         }
+      } else {
+        // singular / non-finite pivot: the reference's QR would hand back Inf/NaN — never leave the caller's
+        // (uninitialised) output untouched
+        for (int q = sl; q < NT; q += SUB) p.thetabar[inst * NT + q] = SENS_NAN;
       }
       if (sl == 0 && p.status_out) p.status_out[inst] = bad;
       __syncwarp(smask);
@@ -2356,6 +2361,8 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         }
         __syncwarp(smask);
       }
+      if (bad)
+        for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = SENS_NAN;
       if (sl == 0 && p.status_out) p.status_out[inst] = bad;
       __syncwarp(smask);
       continue;
@@ -2428,6 +2435,14 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         }
       }
       __syncwarp(smask);
+    }
+    if (bad) {   // a failed factorisation leaves NaN in every requested output of this instance
+      if (p.dzdtheta)
+        for (long long i = sl; i < (long long)NZ * NT; i += SUB) p.dzdtheta[inst * NT * NZ + i] = SENS_NAN;
+      if (p.thetabar)
+        for (int q = sl; q < NT; q += SUB) p.thetabar[inst * NT + q] = SENS_NAN;
+      if (p.z_p)
+        for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = SENS_NAN;
     }
     if (sl == 0 && p.status_out) p.status_out[inst] = bad;
     __syncwarp(smask);

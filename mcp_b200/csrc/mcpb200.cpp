@@ -162,6 +162,19 @@ struct mcpb200_problem {
 
 namespace {
 
+// Restores the caller's current device on EVERY exit path of an entry point that hops over the shards' devices.
+struct DeviceGuard {
+  int cur = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+      cur = -1;
+      cudaGetLastError();
+    }
+  }
+  ~DeviceGuard() {
+    }
+};
+
 int set_err(mcpb200_problem* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   g_global_error = msg;
@@ -307,7 +320,10 @@ std::string nvrtc_to_cubin(const std::string& src, const std::string& name, bool
 int compile_source(mcpb200_problem* h, uint32_t flags) {
   const std::string& src = h->plan.source;
   const std::vector<std::string>& units = h->plan.units;
-  unsigned long long hsh = fnv1a(src + "|sm_100a|v" + std::to_string(MCPB200_VERSION));
+  int nvrtc_major = 0, nvrtc_minor = 0;
+  nvrtcVersion(&nvrtc_major, &nvrtc_minor);
+  unsigned long long hsh = fnv1a(src + "|sm_100a|v" + std::to_string(MCPB200_VERSION) + "|nvrtc" + std::to_string(nvrtc_major) + "." +
+                                 std::to_string(nvrtc_minor) + "|std=c++17,-default-device,-lineinfo");
   for (const std::string& u : units) hsh = hsh * 1099511628211ULL ^ fnv1a(u);
   char key[32];
   snprintf(key, sizeof key, "%016llx", hsh);
@@ -395,8 +411,10 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
   CUDA_TRY(h, cudaFree(0));  // force the primary context
   Driver& D = driver();
   if (!D.ok) return set_err(h, MCPB200_ERR_CUDA, D.err.empty() ? "CUDA driver unavailable" : D.err);
-  auto& slot = h->dev[dev];
-  if (!slot) {
+  auto it = h->dev.find(dev);
+  if (it == h->dev.end() || !it->second) {
+    // built in a local and inserted only after every step succeeded: a failure (not an sm_100 device, module load,
+    // allocation) must not leave a null entry behind for mcpb200_destroy / mcpb200_get_timing to trip over
     auto st = std::make_unique<DeviceState>();
     st->dev = dev;
     cudaDeviceProp prop;
@@ -428,9 +446,9 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
     CUDA_TRY(h, cudaEventCreate(&st->ev_d2h1));
     CUDA_TRY(h, cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     if (st->counters.ensure(64)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(counters) failed");
-    slot = std::move(st);
+    it = h->dev.insert_or_assign(dev, std::move(st)).first;
   }
-  *out = slot.get();
+  *out = it->second.get();
   return MCPB200_OK;
 }
 
@@ -592,9 +610,10 @@ int mcpb200_create(const mcpb200_problem_desc* desc, uint32_t flags, mcpb200_han
 
 int mcpb200_destroy(mcpb200_handle h) {
   if (!h) return MCPB200_OK;
+  DeviceGuard device_guard;
   for (auto& kv : h->dev) {
     DeviceState* st = kv.second.get();
-    if (cudaSetDevice(st->dev) != cudaSuccess) continue;
+    if (!st || cudaSetDevice(st->dev) != cudaSuccess) continue;
     for (DevBuf* b : {&st->scratch, &st->state, &st->counters, &st->deferred, &st->steps_tmp, &st->theta, &st->x, &st->y, &st->s, &st->kkt, &st->eps, &st->outer,
                       &st->status, &st->steps, &st->big0, &st->big1, &st->big2, &st->big3})
       b->release();
@@ -639,6 +658,7 @@ int mcpb200_get_info(mcpb200_handle h, mcpb200_info* info) {
   info->cache_hit = h->cache_hit;
   info->flops_per_newton_step_band = P.flops_band;
   for (auto& kv : h->dev) {
+    if (!kv.second) continue;
     info->regs_solve = kv.second->regs_solve;
     info->regs_sens = kv.second->regs_sens;
   }
@@ -662,11 +682,10 @@ int mcpb200_get_timing(mcpb200_handle h, mcpb200_timing* t) {
   out.solved = 0;
   out.pass0_ms = 0;
   out.deferred = 0;
-  int cur = -1;
-  cudaGetDevice(&cur);
+  DeviceGuard device_guard;
   for (int dev : h->last_devs) {
     auto it = h->dev.find(dev);
-    if (it == h->dev.end() || !it->second->timed) continue;
+    if (it == h->dev.end() || !it->second || !it->second->timed) continue;
     DeviceState* st = it->second.get();
     CUDA_TRY(h, cudaSetDevice(dev));
     CUDA_TRY(h, cudaEventSynchronize(st->ev1));
@@ -688,7 +707,6 @@ int mcpb200_get_timing(mcpb200_handle h, mcpb200_timing* t) {
     out.deferred += (int64_t)c[3];
     out.launches += st->launches;
   }
-  if (cur >= 0) cudaSetDevice(cur);
   *t = out;
   return MCPB200_OK;
 }
@@ -852,8 +870,7 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
     cudaEventElapsedTime(&h2d[i], st->ev_h2d0, st->ev_h2d1);
     cudaEventElapsedTime(&d2h[i], st->ev1, st->ev_d2h1);
   };
-  int cur = -1;
-  cudaGetDevice(&cur);
+  DeviceGuard device_guard;
   if (shards.size() == 1) {
     work(0);
   } else {
@@ -861,7 +878,6 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
     for (size_t i = 0; i < shards.size(); ++i) ts.emplace_back(work, i);
     for (auto& t : ts) t.join();
   }
-  if (cur >= 0) cudaSetDevice(cur);
   for (size_t i = 0; i < shards.size(); ++i) {
     if (rcs[i]) return set_err(h, rcs[i], "device " + std::to_string(shards[i].dev) + ": " + errs[i]);
     h->last_devs.push_back(shards[i].dev);
@@ -890,8 +906,7 @@ int mcpb200_sensitivities(mcpb200_handle h, int64_t B, const double* theta, cons
   if (!theta_p) P = 0;
   // single device per call is enough for the sensitivities host path; shard sequentially over the devices
   std::vector<Shard> shards = make_shards(h->devices, B);
-  int cur = -1;
-  cudaGetDevice(&cur);
+  DeviceGuard device_guard;
   for (const Shard& sh : shards) {
     DeviceState* st = nullptr;
     int rc = device_state(h, sh.dev, &st);
@@ -931,7 +946,6 @@ int mcpb200_sensitivities(mcpb200_handle h, int64_t B, const double* theta, cons
     CUDA_TRY(h, cudaStreamSynchronize(sm));
     h->last_devs.push_back(sh.dev);
   }
-  if (cur >= 0) cudaSetDevice(cur);
   return MCPB200_OK;
 }
 

@@ -188,6 +188,12 @@ def _sens_call(mcp, θ, sol: Solution, want_jac=False, zbar=None, θ_p=None):
         raise ValueError("Missing sensitivities. Set `compute_sensitivities = true` when constructing the "
                          "PrimalDualMCP.")
     h.check(rc)
+    if np.any(st != 0):
+        # a singular / non-finite KKT matrix at the returned point: the kernel NaN-fills those instances' outputs
+        # (the reference's dense QR, `src/AutoDiff.jl:39`, would hand back Inf/NaN or throw)
+        import warnings
+        warnings.warn(f"sensitivities: the KKT matrix is singular for {int(np.count_nonzero(st))} of {B} instance(s); "
+                      "their outputs are NaN", RuntimeWarning, stacklevel=3)
     return jac, tb, zp, st, single
 
 

@@ -27,8 +27,9 @@ _FMT = {
 }
 
 
-def _compile(ir, roots, name):
-    """Python function (x, y, th) -> list of the values of `roots`."""
+def _compile(ir, roots, name, extended=False):
+    """Python function (x, y, th) -> list of the values of `roots`.  `extended`: transcendental nodes go through
+    numpy (dtype-preserving) instead of `math`, so `numpy.longdouble` inputs stay in extended precision."""
     roots = [int(r) for r in roots]
     need = np.zeros(len(ir.op), dtype=bool)
     stack = list(set(roots))
@@ -59,6 +60,8 @@ def _compile(ir, roots, name):
     src = "\n".join(lines).replace("inf", "_inf").replace("nan", "_nan")
     env = {"_sqrt": math.sqrt, "_exp": math.exp, "_log": math.log, "_sin": math.sin, "_cos": math.cos,
            "_inf": math.inf, "_nan": math.nan}
+    if extended:
+        env.update(_sqrt=np.sqrt, _exp=np.exp, _log=np.log, _sin=np.sin, _cos=np.cos)
     exec(compile(src, f"<ir:{name}>", "exec"), env)
     return env[name]
 
@@ -66,14 +69,15 @@ def _compile(ir, roots, name):
 class OracleMCP:
     """CPU counterpart of `struct PrimalDualMCP` (`src/mcp.jl:13-24`)."""
 
-    def __init__(self, ir):
+    def __init__(self, ir, extended=False):
         self.ir = ir
+        self.extended = extended
         self.nx, self.ny, self.ntheta = ir.nx, ir.ny, ir.ntheta
         self.unconstrained_dimension, self.constrained_dimension = ir.nx, ir.ny
         self.n = ir.nx + 2 * ir.ny
-        self._gh = _compile(ir, ir.gh_nodes, "gh")
-        self._jz = _compile(ir, ir.jz_nodes, "jz")
-        self._jt = _compile(ir, ir.jt_nodes, "jt") if ir.jt_nodes is not None else None
+        self._gh = _compile(ir, ir.gh_nodes, "gh", extended)
+        self._jz = _compile(ir, ir.jz_nodes, "jz", extended)
+        self._jt = _compile(ir, ir.jt_nodes, "jt", extended) if ir.jt_nodes is not None else None
         nx, ny = self.nx, self.ny
         k = np.arange(ny)
         # ∇F_z pattern: IR block, then -I, diag(s), diag(y)

@@ -540,3 +540,45 @@ def test_in_library_multi_device_sharding(lane_game):
     np.testing.assert_array_equal(one.x, two.x)          # same kernel, same inputs ⇒ bit-identical
     np.testing.assert_array_equal(one.y, two.y)
     assert t["launches"] == 4 and t["solved"] == int((one.status == 0).sum())   # 2 passes on each of 2 devices
+
+
+def test_sensitivities_singular_instance_is_nan(readme_mcp):
+    """A singular KKT matrix at the supplied point (y = s = 0 ⇒ D = 0/0) must come back as NaN plus a warning, never as
+    whatever the caller's output buffer held (the reference's QR, `src/AutoDiff.jl:39`, hands back non-finite values)."""
+    from mcp_b200 import solve_jacobian_θ, solve_pullback, solve_pushforward
+    from mcp_b200.solver import Solution
+    Θ = problems.readme_qp_thetas(4, seed=3)
+    sol = solve(InteriorPoint(), readme_mcp, Θ)
+    bad = Solution(sol.status.copy(), sol.x.copy(), sol.y.copy(), sol.s.copy(), sol.kkt_error, sol.ϵ, sol.outer_iters,
+                   sol.newton_steps)
+    bad.y[:, 1] = 0.0
+    bad.s[:, 1] = 0.0
+    with pytest.warns(RuntimeWarning, match="singular"):
+        g = solve_pullback(readme_mcp, bad, Θ, 2 * bad.x, 2 * bad.y, None)
+    assert np.all(np.isnan(g[:, 1])) and np.all(np.isfinite(g[:, [0, 2, 3]]))
+    with pytest.warns(RuntimeWarning):
+        J = solve_jacobian_θ(readme_mcp, bad, Θ)
+    assert np.all(np.isnan(J[:, :, 1])) and np.all(np.isfinite(J[:, :, 0]))
+    with pytest.warns(RuntimeWarning):
+        xp, yp, sp = solve_pushforward(readme_mcp, bad, Θ, np.tile(np.eye(2)[:, :, None], (1, 1, 4)))
+    assert np.all(np.isnan(xp[:, :, 1])) and np.all(np.isfinite(xp[:, :, 2]))
+
+
+def test_gpu_solutions_satisfy_independent_kkt(lane_game):
+    """GPU lane-change solutions checked against the problem definition written independently of the tracer
+    (`oracle/independent_problems.py`): the reference's own `check_solution` assertions (`test/runtests.jl:30-38`)
+    at the scale of tol = 1e-6, with G and H evaluated by torch autograd straight from the reference's formulas."""
+    from oracle.independent_problems import IndependentTrajectoryGame
+    ind = IndependentTrajectoryGame("lane_change", 2, 10)
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(32, seed=9)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    checked = 0
+    for b in np.nonzero(sol.status == 0)[0]:
+        F = ind.F(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], 0.0)
+        G, Hms, sy = F[:200], F[200:450], F[450:]
+        H = Hms + sol.s[:, b]
+        assert np.max(np.abs(G)) <= 1e-5 and np.min(H) >= -1e-5 and np.min(sol.y[:, b]) >= 0
+        assert np.max(np.abs(Hms)) <= 1e-5 and np.max(sy) <= 1e-5 and float(sol.y[:, b] @ H) <= 1e-3
+        checked += 1
+    assert checked >= 28
