@@ -115,6 +115,14 @@ __device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, F
 // CTA-shared tables (first SHARED_TABLE_DOUBLES doubles of dynamic shared memory): ROWPTR_S[NRED+1]
 // (first dest of each condensed row) and CPOS_S[ND] (circular window position of each dest).
 // ------------------------------------------------------------------------------------------------
+// Geometry of the register-resident window (see band_solve): NPART lanes per window row, PW positions each.
+// WR + 1 row slots: the spare one lets the row that enters the window be staged a whole pivot step before it is needed.
+#define BS_RS (WR + 1)
+#define BS_NPART ((BS_RS <= SUB) ? ((SUB / BS_RS) >= 4 ? 4 : ((SUB / BS_RS) >= 2 ? 2 : 1)) : 1)
+#define BS_PW ((((WC + 1 + BS_NPART - 1) / BS_NPART) + 1) & ~1)
+#define BS_REGWIN (REGWIN && BS_RS <= SUB && BS_PW <= REGWIN_PW_MAX)
+#define BS_PREFETCH_AT ((NRED > 8) ? 8 : 1)   // pivot steps before the end of the factorisation at which Uᵀ is prefetched into the L2
+
 __device__ __forceinline__ void load_shared_tables(double* smem_base, bool transposed = false) {
   int* rowptr = reinterpret_cast<int*>(smem_base);
   unsigned short* cpos = reinterpret_cast<unsigned short*>(rowptr + NRED + 1);
@@ -122,13 +130,31 @@ __device__ __forceinline__ void load_shared_tables(double* smem_base, bool trans
   if (transposed) {   // the column-major view of the same non-zeros: the factorisation then sees Cᵀ
     for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = DT_ROWPTR[i];
     for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)DT_CPOS[i];
-    __syncthreads();
-    return;
-  }
+  } else
 #endif
-  for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = D_ROWPTR[i];
-  for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)D_CPOS[i];
+  {
+    for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = D_ROWPTR[i];
+    for (int i = threadIdx.x; i < ND; i += blockDim.x) cpos[i] = (unsigned short)D_CPOS[i];
+  }
   __syncthreads();
+#if BS_REGWIN
+  // The register window wants each non-zero's position RELATIVE to the first column of the window at the moment its
+  // row enters: row r enters relative to column max(0, r − KL), so rel = col − max(0, r − KL) ∈ [0, WC).  Stored in
+  // place of the circular position (col mod WC), from which it follows.
+  // Rows 0 … WR are in the initial window (relative to column 0); row r > WR is staged at the end of pivot step
+  // r − WR − 1, relative to column r − WR, one step before its first column (r − WR + 1 = r − KL) is eliminated: its
+  // positions are 1 … WC.  Row WR itself sits at positions 1 … WC of the initial window.
+  for (int r = threadIdx.x; r < NRED; r += blockDim.x) {
+    const int first = (r > WR) ? (r - WR) % WC : 0;
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      int d = (int)cpos[e] - first;
+      if (d < 0) d += WC;
+      if (r >= WR && d == 0) d = WC;   // (col mod WC cannot tell WC from 0; these rows have no entry at position 0)
+      cpos[e] = (unsigned short)d;
+    }
+  }
+  __syncthreads();
+#endif
 }
 
 // Named barrier among the NW warps that share one instance (ids 1…15; id 0 is __syncthreads).
@@ -159,17 +185,17 @@ __device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
     const int tb = CH_T[c], te = CH_T[c + 1];
 #pragma unroll 4
     for (int t = tb + wl; t < te; t += WL) {
-      const int4 ti = T_I[t];  // {a, b, k, -}
-      double v = T_COEF[t] * opval(ti.x, jv, th);
+      const TI_T ti = T_I[t];  // {a, b, k, -}
+      double v = T_COEF_AT(t) * opval(ti.x, jv, th);
       if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
       tmp[t - tb] = v;
     }
     if constexpr (NW > 1) wide_bar(bar_id, NW * 32); else __syncwarp(smask);
     for (int d = CH_D[c] + wl; d < CH_D[c + 1]; d += WL) {
       const int tp = D_TP[d];
-      const int t1 = D_TP[d + 1] & 0x7fffffff;
-      double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
-      for (int t = tp & 0x7fffffff; t < t1; ++t) acc += tmp[t - tb];
+      const int t1 = D_TP[d + 1] & D_TP_MASK;
+      double acc = D_BASE_AT(d) + ((tp < 0) ? tol : 0.0);  // sign bit of D_TP marks a diagonal dest
+      for (int t = tp & D_TP_MASK; t < t1; ++t) acc += tmp[t - tb];
       __stcg(Cval + d, acc);   // streaming scratch: keep L1 for the assembly tables
     }
     if constexpr (NW > 1) wide_bar(bar_id, NW * 32); else __syncwarp(smask);
@@ -177,11 +203,11 @@ __device__ __forceinline__ void assemble_matrix(double* RS Cval, double* RS tmp,
 #else
   for (int d = wl; d < ND; d += WL) {
     const int tp = D_TP[d];
-    const int t1 = D_TP[d + 1] & 0x7fffffff;
-    double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
-    for (int t = tp & 0x7fffffff; t < t1; ++t) {
-      const int4 ti = T_I[t];
-      double v = T_COEF[t] * opval(ti.x, jv, th);
+    const int t1 = D_TP[d + 1] & D_TP_MASK;
+    double acc = D_BASE_AT(d) + ((tp < 0) ? tol : 0.0);
+    for (int t = tp & D_TP_MASK; t < t1; ++t) {
+      const TI_T ti = T_I[t];
+      double v = T_COEF_AT(t) * opval(ti.x, jv, th);
       if (ti.z >= 0) v *= dinv[ti.z] * opval(ti.y, jv, th);
       acc += v;
     }
@@ -195,6 +221,7 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_
   const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");  // L2 only
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -276,11 +303,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   constexpr int WPL = (WS + SUB - 1) / SUB;
 
   // 2-D register layout: NPART lanes per window row, PW (even) consecutive positions each
-  constexpr int NPART = (WR <= SUB) ? ((SUB / WR) >= 4 ? 4 : ((SUB / WR) >= 2 ? 2 : 1)) : 1;
-  constexpr int PW = (((WC + NPART - 1) / NPART) + 1) & ~1;
-  constexpr int WCP = PW * NPART;               // padded matrix width
+  constexpr int NPART = BS_NPART;
+  constexpr int PW = BS_PW;
+  constexpr int WCP = PW * NPART;               // padded matrix width (≥ WC + 1)
   constexpr int ES = (WCP + NRHS + 3) & ~1;     // stride of the publish / staging rows (even, one pair of slack)
-  if constexpr (REGWIN && WR <= SUB && PW <= REGWIN_PW_MAX) {
+  if constexpr (BS_REGWIN) {
     // ============ register-resident window ==========================================================
     // Window rows live in REGISTERS for their whole life in the window, each row split over NPART lanes:
     // lane (row, part) holds a[i] = the entry in column j + part·PW + i — a layout relative to the pivot
@@ -291,9 +318,23 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     // with aligned 128-bit broadcast loads; shared memory otherwise only stages the entering row.
     // Why: with the window itself in shared memory (variant below) the smem pipe sat at 60 % of peak
     // re-loading/re-storing rows, and broadcasting by shuffle costs the same crossbar as many wavefronts.
-    const bool active = sl < WR * NPART;
-    const int row = sl % WR;
-    const int part = active ? sl / WR : 0;
+    // lane = row·NPART + part: the parts of one row sit in the same quarter-warp, so the two-lane 128-bit publish /
+    // reload of a row costs one shared-memory wavefront per instruction instead of one per lane.
+    //
+    // r2 — the pivot step is a latency chain (ncu: ≈1150 cycles per step for ≈130 issued instructions, six dependent
+    // shared-memory / shuffle round trips), so the loop is organised to take work OFF that chain:
+    //   * BS_RS = WR + 1 row slots: the spare slot receives the next row a whole step before its first column is
+    //     eliminated, so its staging (scatter → barrier → reload) is off the chain.  A freshly loaded row has a
+    //     structural zero in the next pivot column; `head` (the lane's pivot-column entry, kept apart from a[0]) is set
+    //     to zero for it, so neither the pivot search nor the multipliers wait for the reload;
+    //   * the pivot row is published as soon as the pivot is known and its broadcast loads are issued before the
+    //     reciprocal / multiplier arithmetic, which then runs in their shadow;
+    //   * positions relative to the entering window are precomputed (load_shared_tables), the pivot's validity is read
+    //     off the reduction key, the reciprocal is MUFU + two Newton steps, right-hand sides move straight between
+    //     registers and `sol`, and every per-step address is a running pointer.
+    const bool active = sl < BS_RS * NPART;
+    const int row = active ? sl / NPART : BS_RS;
+    const int part = active ? sl % NPART : 0;
     double a[PW], rh[NRHS];
     double* Pb = W;       // published pivot row: WCP matrix positions, then the RHS
     double* E = W + ES;   // two staging rows, alternating between steps
@@ -301,7 +342,8 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     for (int i = 0; i < PW; ++i) a[i] = 0.0;
 #pragma unroll
     for (int q = 0; q < NRHS; ++q) rh[q] = 0.0;
-    for (int r = 0; r < WR; ++r) {  // rows 0 … WR-1, relative to column 0 (their columns are < WC: no wrap)
+    constexpr int NFILL = (BS_RS < NRED) ? BS_RS : NRED;
+    for (int r = 0; r < NFILL; ++r) {  // rows 0 … WR, relative to column 0
       for (int q = sl; q < ES; q += SUB) E[q] = 0.0;
       __syncwarp(smask);
       for (int e = rowptr[r] + sl; e < rowptr[r + 1]; e += SUB) E[cpos[e]] = cval_at(e);
@@ -320,60 +362,65 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
       }
       __syncwarp(smask);
     }
-    int cj1 = (1 == WC) ? 0 : 1;  // (j+1) % WC: circular position of the column that becomes relative 0 next
+    const bool lane_pub = active && part == 0;
+    double head = a[0];                            // my row's entry in the pivot column (part-0 lanes)
+    int e_lo = (BS_RS < NRED) ? rowptr[BS_RS] : 0;   // first non-zero of the row staged at the end of step 0 (row WR + 1)
+    const int* rpj = rowptr + ((BS_RS < NRED) ? BS_RS + 1 : 0);   // → rowptr[(row being staged) + 1]
+    double* UTj = UT + (size_t)sl * (UTS + 1);     // lane t writes U[j][j+t] to UT[(j+t)·UTS + t] = UTj[0], UTj += UTS
+    double* solj = sol;                            // → sol[j]; the staged row's right-hand side is solj[BS_RS]
+    double* Eb = E;
+    double* Eo = E + ES;
+    int left = NRED;                               // NRED − j
 #pragma unroll 1
-    for (int j = 0; j < NRED; ++j) {
-      double* Eb = E + (j & 1) * ES;
-      const int ienter = j + WR;
-      int e0 = 0, e1 = 0;
-      if (ienter < NRED) {
-        e0 = rowptr[ienter];
-        e1 = rowptr[ienter + 1];
+    for (; left > 0; --left) {
+      if (left == BS_PREFETCH_AT) {
+        // The back substitution reads Uᵀ from its END; the rows written first (one factorisation ago for the L2: all
+        // resident instances stream ~100 MB through it in that time) are the ones most likely to have been evicted.
+        // Ask for the whole array now, a few thousand cycles ahead, so the sweep finds it in the L2.
+        for (int i = sl; i < (NRED * UTS + 15) / 16; i += SUB) prefetch_l2(UT + (size_t)i * 16);
       }
+      const bool entering = left > BS_RS;           // row j + WR + 1 exists
+      const int e_hi = entering ? *rpj : e_lo;
       double pre[CPW];
+      int prel[CPW];
 #pragma unroll
-      for (int k = 0; k < CPW; ++k) {
-        const int e = e0 + sl + SUB * k;
-        pre[k] = (e < e1) ? cval_at(e) : 0.0;
+      for (int k = 0; k < CPW; ++k) {   // prefetch the staged row's non-zeros (consumed at the end of the step)
+        const int e = e_lo + sl + SUB * k;
+        prel[k] = -1;
+        pre[k] = 0.0;
+        if (e < e_hi) {
+          pre[k] = cval_at(e);
+          prel[k] = cpos[e];
+        }
       }
-      for (int q = sl; q < ES; q += SUB) Eb[q] = 0.0;
-      // ---- pivot search over column j: max |a| on a 12-bit-truncated mantissa, row in the low byte ----
+      for (int q = sl; q < ES; q += SUB) Eb[q] = 0.0;   // (this buffer was last read two steps ago)
+      // ---- pivot search over column j: max |head| on a 12-bit-truncated mantissa, row in the low byte ----
       unsigned key = 0;
-      if (active && part == 0) key = ((unsigned)__double2hiint(fabs(a[0])) & 0xffffff00u) | (unsigned)(255 - row);
+      if (lane_pub) key = ((unsigned)__double2hiint(fabs(head)) & 0xffffff00u) | (unsigned)(255 - row);
       const unsigned best = __reduce_max_sync(smask, key);
+      // zero / denormal (exponent field 0), Inf / NaN or ≥ 2^1022 (reciprocal not representable): the reference's
+      // `:failed` retcode branch (src/solver.jl:84-88)
+      if (best < 0x00100000u || best >= 0x7fd00000u) return 1;
       const int p = 255 - (int)(best & 0xffu);
-      const double piv = __shfl_sync(smask, a[0], p, SUB);
-      if (!(fabs(piv) > 0.0) || !(fabs(piv) <= DBL_MAX_)) return 1;  // zero, NaN or Inf pivot
-      const double rp = 1.0 / piv;
-      const double a0row = __shfl_sync(smask, a[0], row, SUB);       // my row's entry in the pivot column
-      double nx = __shfl_sync(smask, a[0], (sl + WR) % SUB, SUB);    // first entry of my row's next part
-      if (part == NPART - 1) nx = 0.0;
-      const double m = (active && row != p) ? -(a0row * rp) : 0.0;
-      // ---- publish the pivot row ----------------------------------------------------------------------------
-      if (active && row == p) {
+      const bool mine = active && row == p;
+      // ---- publish the pivot row at once; its right-hand side retires straight into sol -------------------
+      if (mine) {
         double2* dst = reinterpret_cast<double2*>(Pb + part * PW);
 #pragma unroll
         for (int k = 0; k < PW / 2; ++k) dst[k] = make_double2(a[2 * k], a[2 * k + 1]);
         if (part == 0) {
 #pragma unroll
-          for (int q = 0; q < NRHS; ++q) Pb[WCP + q] = rh[q];
+          for (int q = 0; q < NRHS; ++q) {
+            Pb[WCP + q] = rh[q];
+            solj[q * NRED] = rh[q];
+          }
         }
       }
       __syncwarp(smask);
-      // ---- retire it: U row j goes out transposed (coalesced over the lanes), its RHS into sol ------------
-      {
-        const int tmax = min(WC - 1, NRED - 1 - j);
-#pragma unroll
-        for (int k = 0; k < CPW; ++k) {
-          const int t = sl + SUB * k;
-          if (t <= tmax) __stcg(UT + (size_t)(j + t) * UTS + t, (t == 0) ? rp : Pb[t]);
-        }
-        if (sl < NRHS) sol[sl * NRED + j] = Pb[WCP + sl];
-      }
-      // ---- eliminate column j and slide the window: a[i] ← a[i+1] − m·u[i+1] ------------------------------
+      // ---- broadcast loads of the pivot row (in flight while the multipliers are computed) ------------------
+      double u[PW + 2], urh[NRHS];
       {
         const double2* up = reinterpret_cast<const double2*>(Pb + part * PW);
-        double u[PW + 2];
 #pragma unroll
         for (int k = 0; k <= PW / 2; ++k) {  // PW/2 + 1 aligned pairs: my part and the first entry of the next
           const double2 v = up[k];
@@ -381,25 +428,51 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
           u[2 * k + 1] = v.y;
         }
 #pragma unroll
-        for (int i = 0; i + 1 < PW; ++i) a[i] = fma(m, u[i + 1], a[i + 1]);
-        a[PW - 1] = (part == NPART - 1) ? 0.0 : fma(m, u[PW], nx);   // last part: column j+WCP enters, zero
-#pragma unroll
-        for (int q = 0; q < NRHS; ++q) rh[q] = fma(m, Pb[WCP + q], rh[q]);
+        for (int q = 0; q < NRHS; ++q) urh[q] = Pb[WCP + q];
       }
-      // ---- the entering row (relative to column j+1) takes over the retired row's lanes -----------------------
-      __syncwarp(smask);
+      double ut_out[CPW];
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
-        const int e = e0 + sl + SUB * k;
-        if (e < e1) {
-          int d = (int)cpos[e] - cj1;
-          if (d < 0) d += WC;
-          Eb[d] = pre[k];
-        }
+        const int t = sl + SUB * k;
+        ut_out[k] = (t < WC) ? Pb[t] : 0.0;
       }
-      if (sl < NRHS && ienter < NRED) Eb[WCP + sl] = sol[sl * NRED + ienter];
+      // ---- pivot, reciprocal, multipliers --------------------------------------------------------------------
+      const double piv = __shfl_sync(smask, head, p * NPART, SUB);
+      double a0row = head;
+      if constexpr (NPART > 1) a0row = __shfl_sync(smask, head, sl - part, SUB);   // my row's entry in the pivot column
+      double rp;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rp) : "d"(piv));   // ~20 bits, then two Newton steps: ≤ 1 ulp
+      {
+        double er = fma(-piv, rp, 1.0);
+        rp = fma(rp, er, rp);
+        er = fma(-piv, rp, 1.0);
+        rp = fma(rp, er, rp);
+      }
+      const double m = (active && !mine) ? -(a0row * rp) : 0.0;
+      double nx = 0.0;
+      if constexpr (NPART > 1) {
+        nx = __shfl_sync(smask, a[0], (sl + 1) % SUB, SUB);     // first entry of my row's next part
+        if (part == NPART - 1) nx = 0.0;
+      }
+      // ---- U row j goes out transposed (coalesced over the lanes) ------------------------------------------
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int t = sl + SUB * k;
+        if (t < WC && t < left) __stcg(UTj + (size_t)k * SUB * (UTS + 1), (t == 0) ? rp : ut_out[k]);
+      }
+      // ---- eliminate column j and slide the window: a[i] ← a[i+1] − m·u[i+1] ------------------------------
+#pragma unroll
+      for (int i = 0; i + 1 < PW; ++i) a[i] = fma(m, u[i + 1], a[i + 1]);
+      a[PW - 1] = (part == NPART - 1) ? 0.0 : fma(m, u[PW], nx);   // last part: column j+WCP enters, zero
+#pragma unroll
+      for (int q = 0; q < NRHS; ++q) rh[q] = fma(m, urh[q], rh[q]);
+      head = a[0];
+      // ---- the next row (relative to column j+1, first needed at step j+2) takes over the retired row's lanes ----
+#pragma unroll
+      for (int k = 0; k < CPW; ++k)
+        if (prel[k] >= 0) Eb[prel[k]] = pre[k];
       __syncwarp(smask);
-      if (active && row == p) {
+      if (mine) {
         const double2* src = reinterpret_cast<const double2*>(Eb + part * PW);
 #pragma unroll
         for (int k = 0; k < PW / 2; ++k) {
@@ -408,9 +481,18 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
           a[2 * k + 1] = v.y;
         }
 #pragma unroll
-        for (int q = 0; q < NRHS; ++q) rh[q] = Eb[WCP + q];
+        for (int q = 0; q < NRHS; ++q) rh[q] = entering ? solj[q * NRED + BS_RS] : 0.0;
+        head = 0.0;   // structurally zero in column j+1: the search and the multipliers need not wait for the reload
       }
-      cj1 = (cj1 + 1 == WC) ? 0 : cj1 + 1;
+      e_lo = e_hi;
+      if (entering) ++rpj;
+      UTj += UTS;
+      ++solj;
+      {
+        double* t_ = Eb;
+        Eb = Eo;
+        Eo = t_;
+      }
     }
     __syncwarp(smask);
   } else {
@@ -436,10 +518,10 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
       for (int i = sl; i < 2 * STAGE_N; i += SUB) stage[i] = 0.0;
       __syncwarp(smask);
 #pragma unroll 4
-      for (int e = H_PTR[k] + sl; e < H_PTR[k + 1]; e += SUB) hb[H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+      for (int e = H_PTR[k] + sl; e < H_PTR[k + 1]; e += SUB) hb[H_COL[e]] = H_COEF_AT(e) * opval(H_CODE[e], jv, th);
       const double dk = dinv[k];
 #pragma unroll 4
-      for (int e = GK_PTR[k] + sl; e < GK_PTR[k + 1]; e += SUB) gb[GK_ROW[e]] = GK_COEF[e] * opval(GK_CODE[e], jv, th) * dk;
+      for (int e = GK_PTR[k] + sl; e < GK_PTR[k + 1]; e += SUB) gb[GK_ROW[e]] = GK_COEF_AT(e) * opval(GK_CODE[e], jv, th) * dk;
       __syncwarp(smask);
       const double2* hb2 = reinterpret_cast<const double2*>(hb);
 #pragma unroll 1
@@ -580,54 +662,88 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   }
 
   // ---- back substitution: column sweep, x_j = rhs_j / u_jj then rhs_i −= U[i][j] x_j for i < j.
-  // The columns of U (rows of UT) stream back through a RING_D-deep cp.async ring that re-uses the
-  // window's shared memory, so the L2/HBM latency of the scratch is off the critical path.
+  // The right-hand sides live in REGISTERS while they are being updated: lane L owns the rows i ≡ L (mod SUB) of the
+  // dependency window (NACC of them), so one column costs one shared load (the lane's entry of Uᵀ's row j), one
+  // multiply + broadcast by the row's owner and one FMA per accumulator — `sol` is read and written once per row
+  // instead of once per (row, column).  The columns of U (rows of UT) stream back through two cp.async buffers of
+  // BS_CH rows each that re-use the window's shared memory.
   {
+    constexpr int BS_CH = (RING_D >= 2) ? RING_D / 2 : 1;
+    constexpr int NACC = (WC - 1) / SUB + 1;
+    constexpr int CHP = BS_CH * UTS / 2;   // 16-byte pieces per chunk
     double* ring = W;
-    auto issue = [&](int col) {
-      if (col >= 0) {
-        const double* src = UT + (size_t)col * UTS;
-        double* dst = ring + ((NRED - 1 - col) % RING_D) * UTS;
+    // chunk c holds UT rows [lo, lo + BS_CH) with lo = NRED − (c+1)·BS_CH (clipped at 0: the last chunk is partial)
+    auto issue = [&](int c) {
+      const int hi = NRED - c * BS_CH;   // exclusive
+      if (hi > 0) {
+        const int lo = (hi - BS_CH > 0) ? hi - BS_CH : 0;
+        const double* src = UT + (size_t)lo * UTS;
+        double* dst = ring + (c & 1) * (BS_CH * UTS) + (lo - (hi - BS_CH)) * UTS;
+        const int np = (hi - lo) * UTS / 2;
 #pragma unroll
-        for (int k = 0; k < (UTS / 2 + SUB - 1) / SUB; ++k) {
-          const int t2 = sl + SUB * k;  // pair index
-          if (t2 < UTS / 2) cp_async16(dst + 2 * t2, src + 2 * t2);
+        for (int k = 0; k < (CHP + SUB - 1) / SUB; ++k) {
+          const int t2 = sl + SUB * k;
+          if (t2 < np) cp_async16(dst + 2 * t2, src + 2 * t2);
         }
       }
       cp_async_commit();  // (possibly empty) group: keeps the group count uniform
     };
     __syncwarp(smask);
-#pragma unroll 1
-    for (int i = 0; i < RING_D - 1; ++i) issue(NRED - 1 - i);
-#pragma unroll 1
-    for (int j = NRED - 1; j >= 0; --j) {
-      issue(j - (RING_D - 1));
-      cp_async_wait<RING_D - 1>();
-      __syncwarp(smask);
-      const double* Uj = ring + ((NRED - 1 - j) % RING_D) * UTS;
-      const double rd = Uj[0];
-      double ut[CPW];
+    issue(0);
+    issue(1);
+    double acc[NRHS][NACC];
+    int t0 = (((NRED - 1 - sl) % SUB) + SUB) % SUB;   // distance from column j down to my nearest row: row j − t0 is acc[·][0]
 #pragma unroll
-      for (int k = 0; k < CPW; ++k) {
-        const int t = sl + 1 + SUB * k;
-        ut[k] = (t < WC) ? Uj[t] : 0.0;
+    for (int q = 0; q < NRHS; ++q)
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        const int i = NRED - 1 - t0 - SUB * k;
+        acc[q][k] = (i >= 0) ? sol[q * NRED + i] : 0.0;
+      }
+    constexpr int NCHUNK = (NRED + BS_CH - 1) / BS_CH;
+    int own = (NRED - 1) % SUB;   // lane that owns row j
+    // one column: x_j from its owner, then every lane updates the rows it owns inside the dependency window
+    auto column = [&](int j, const double* Uj) {
+      double ut[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) {
+        const int t = t0 + SUB * k;
+        ut[k] = (t < WC) ? Uj[t] : 0.0;   // t == 0: the reciprocal pivot
       }
 #pragma unroll
       for (int q = 0; q < NRHS; ++q) {
-        double xj = 0.0;
-        if (sl == 0) {
-          xj = sol[q * NRED + j] * rd;
-          sol[q * NRED + j] = xj;
-        }
-        xj = __shfl_sync(smask, xj, 0, SUB);
+        const double xj = __shfl_sync(smask, acc[q][0] * ut[0], own, SUB);
 #pragma unroll
-        for (int k = 0; k < CPW; ++k) {
-          const int t = sl + 1 + SUB * k;
-          if (t < WC && t <= j) sol[q * NRED + j - t] = fma(-ut[k], xj, sol[q * NRED + j - t]);
+        for (int k = 0; k < NACC; ++k) {   // rows j − t, t = t0 + SUB·k ∈ [1, WC)
+          const int t = t0 + SUB * k;
+          if (t >= 1 && t < WC) acc[q][k] = fma(-ut[k], xj, acc[q][k]);
+        }
+        if (t0 == 0 && j >= 0) {   // row j is finished: store it, my accumulators move on to rows j − SUB, j − 2·SUB, …
+          sol[q * NRED + j] = xj;
+#pragma unroll
+          for (int k = 0; k + 1 < NACC; ++k) acc[q][k] = acc[q][k + 1];
+          const int inext = j - SUB * NACC;
+          acc[q][NACC - 1] = (inext >= 0) ? sol[q * NRED + inext] : 0.0;
         }
       }
+      t0 = (t0 + SUB - 1) % SUB;
+      own = (own + SUB - 1) % SUB;
+    };
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      cp_async_wait<1>();
       __syncwarp(smask);
+      const double* buf = ring + (c & 1) * (BS_CH * UTS);
+      const int jhi = NRED - 1 - c * BS_CH;
+      // (the last chunk may run past column 0: those virtual columns only touch accumulators of rows that do not
+      // exist and stale ring data; keeping the control flow uniform keeps the shuffles free of re-convergence code)
+#pragma unroll
+      for (int jj = 0; jj < BS_CH; ++jj) column(jhi - jj, buf + (BS_CH - 1 - jj) * UTS);
+      __syncwarp(smask);      // everyone is done with this buffer before it is refilled
+      issue(c + 2);
     }
+    cp_async_wait<0>();
+    __syncwarp(smask);
   }
   return 0;
 }
@@ -914,11 +1030,11 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
     if (t < 256) mcp_eval_const_par(t, x, y, th, gh0);
     __syncthreads();
     for (int k = wid; k < NY; k += DT / 32)
-      for (int e = H_PTR[k] + lane; e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+      for (int e = H_PTR[k] + lane; e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF_AT(e) * opval(H_CODE[e], jv, th);
     for (int d = t; d < ND; d += DT) {
-      const int tp = D_TP[d], t1 = D_TP[d + 1] & 0x7fffffff;
-      double a0 = D_BASE[d] + ((tp < 0) ? tol : 0.0);
-      for (int q = tp & 0x7fffffff; q < t1; ++q) a0 += T_COEF[q] * opval(T_I[q].x, jv, th);
+      const int tp = D_TP[d], t1 = D_TP[d + 1] & D_TP_MASK;
+      double a0 = D_BASE_AT(d) + ((tp < 0) ? tol : 0.0);
+      for (int q = tp & D_TP_MASK; q < t1; ++q) a0 += T_COEF_AT(q) * opval(T_I[q].x, jv, th);
       __stcg(Gc + D_CPOS[d] * D3_GLD + D_ROW[d], a0);
     }
     __syncthreads();
@@ -1196,7 +1312,7 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
     mcp_eval_const_par(t, x, y, th, gh0);
     __syncthreads();
     for (int k = (t >> 5); k < NY; k += DT / 32)
-      for (int e = H_PTR[k] + (t & 31); e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
+      for (int e = H_PTR[k] + (t & 31); e < H_PTR[k + 1]; e += 32) Hc[k * HCS + H_COL[e]] = H_COEF_AT(e) * opval(H_CODE[e], jv, th);
     __syncthreads();
     bool parked = false;
     while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
@@ -1216,13 +1332,13 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
           for (int u = 0; u < 4; ++u) {
             const int d = min(d0 + u * DT, ND - 1);
             tp[u] = D_TP[d];
-            t1[u] = D_TP[d + 1] & 0x7fffffff;
-            acc[u] = D_BASE[d] + ((tp[u] < 0) ? tol : 0.0);
+            t1[u] = D_TP[d + 1] & D_TP_MASK;
+            acc[u] = D_BASE_AT(d) + ((tp[u] < 0) ? tol : 0.0);
             rc[u] = D_ROW[d] * WS + D_CPOS[d];
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            for (int q = tp[u] & 0x7fffffff; q < t1[u]; ++q) acc[u] += T_COEF[q] * opval(T_I[q].x, jv, th);
+            for (int q = tp[u] & D_TP_MASK; q < t1[u]; ++q) acc[u] += T_COEF_AT(q) * opval(T_I[q].x, jv, th);
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (d0 + u * DT < ND) W[rc[u]] = acc[u];
@@ -1517,7 +1633,7 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
           double acc = 0.0;
           if (r_ < NRED) {
             const int e0 = R_PTR[r_], e1 = R_PTR[r_ + 1], mid = e0 + (e1 - e0 + 1) / 2;
-            for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
+            for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += R_COEF_AT(e) * opval(R_CODE[e], jv, th) * w[R_K[e]];
           }
           part[hf * 128 + r_] = acc;
           __syncthreads();
@@ -1526,9 +1642,9 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
         // ---- direct part of C: G_x + tol·I (one dest per matrix entry, row-sorted) ---------------------------
         for (int d = t; d < ND; d += DT) {
           const int tp = D_TP[d];
-          const int t1 = D_TP[d + 1] & 0x7fffffff;
-          double acc = D_BASE[d] + ((tp < 0) ? tol : 0.0);
-          for (int q = tp & 0x7fffffff; q < t1; ++q) acc += T_COEF[q] * opval(T_I[q].x, jv, th);
+          const int t1 = D_TP[d + 1] & D_TP_MASK;
+          double acc = D_BASE_AT(d) + ((tp < 0) ? tol : 0.0);
+          for (int q = tp & D_TP_MASK; q < t1; ++q) acc += T_COEF_AT(q) * opval(T_I[q].x, jv, th);
           W[D_ROW[d] * WS + D_CPOS[d]] = acc;
         }
         // ---- Schur part: C −= Σ_k (G_y[:,k] D⁻¹_k) ⊗ H_x[k,:], register-tiled over blocks of DKB constraints ----
@@ -1546,8 +1662,8 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
               const int kk = t >> 5, k = k0 + kk, ln = t & 31;  // warp kk stages constraint k0+kk
               if (k < NY) {
                 const double dk = dinv[k];
-                for (int e = H_PTR[k] + ln; e < H_PTR[k + 1]; e += 32) hbs[kk * DNP + H_COL[e]] = H_COEF[e] * opval(H_CODE[e], jv, th);
-                for (int e = GK_PTR[k] + ln; e < GK_PTR[k + 1]; e += 32) gbs[kk * DNP + GK_ROW[e]] = GK_COEF[e] * opval(GK_CODE[e], jv, th) * dk;
+                for (int e = H_PTR[k] + ln; e < H_PTR[k + 1]; e += 32) hbs[kk * DNP + H_COL[e]] = H_COEF_AT(e) * opval(H_CODE[e], jv, th);
+                for (int e = GK_PTR[k] + ln; e < GK_PTR[k + 1]; e += 32) gbs[kk * DNP + GK_ROW[e]] = GK_COEF_AT(e) * opval(GK_CODE[e], jv, th) * dk;
               }
             }
             __syncthreads();
@@ -1639,7 +1755,7 @@ extern "C" __global__ void __launch_bounds__(DT, 2) mcp_solve_kernel(const Solve
             double acc = 0.0;
             if (r_ < NY) {
               const int e0 = H_PTR[r_], e1 = H_PTR[r_ + 1], mid = e0 + (e1 - e0 + 1) / 2;
-              for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
+              for (int e = hf ? mid : e0; e < (hf ? e1 : mid); ++e) acc += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
             }
             part[hf * 128 + r_] = acc;
             __syncthreads();
@@ -2118,7 +2234,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     for (int i = sl; i < NRED; i += SUB) {
       double r = -g[R_GROW[i]];
 #pragma unroll 4
-      for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * w[R_K[e]];
+      for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF_AT(e) * opval(R_CODE[e], jv, th) * w[R_K[e]];
       sol[i] = r;
     }
     __syncwarp(smask);  // G (aliased onto the window) is dead from here on: the window becomes scratch
@@ -2140,7 +2256,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
       for (int k = sl; k < NY; k += SUB) {
         double hx = 0.0;
 #pragma unroll 4
-        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
+        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
         const double dy = w[k] - dinv[k] * hx;
         const double f3 = s[k] * y[k] - eps;
         w[k] = dy;
@@ -2282,7 +2398,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
       __syncwarp(smask);
       for (int k = sl; k < NY; k += SUB) {
         const double vk = wq[k];
-        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) atomicAdd(&sol[H_COL[e]], -H_COEF[e] * opval(H_CODE[e], jv, th) * vk);
+        for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) atomicAdd(&sol[H_COL[e]], -H_COEF_AT(e) * opval(H_CODE[e], jv, th) * vk);
       }
       __syncwarp(smask);
       assemble_matrix(Cval, W, jv, th, dinv, 0.0, sl, smask);
@@ -2292,7 +2408,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         for (int i = sl; i < NRED; i += SUB) {
           const double li = sol[i];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
-            atomicAdd(&wq[R_K[e]], -dinv[R_K[e]] * R_COEF[e] * opval(R_CODE[e], jv, th) * li);
+            atomicAdd(&wq[R_K[e]], -dinv[R_K[e]] * R_COEF_AT(e) * opval(R_CODE[e], jv, th) * li);
         }
         __syncwarp(smask);
         for (int q = sl; q < NT; q += SUB) {
@@ -2300,7 +2416,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
           for (int e = Q_PTR[q]; e < Q_PTR[q + 1]; ++e) {
             const int row = Q_ROW[e];
             const double lam = (row < NX) ? sol[IPERM[row]] : wq[row - NX];
-            acc -= Q_COEF[e] * opval(Q_CODE[e], jtv, th) * lam;
+            acc -= Q_COEF_AT(e) * opval(Q_CODE[e], jtv, th) * lam;
           }
           p.thetabar[inst * NT + q] = acc;
         }
@@ -2326,7 +2442,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         __syncwarp(smask);
         for (int q = 0; q < NT; ++q) {
           for (int e = Q_PTR[q] + sl; e < Q_PTR[q + 1]; e += SUB) {   // rows within one column are distinct: no atomics
-            const double f = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
+            const double f = -Q_COEF_AT(e) * opval(Q_CODE[e], jtv, th);
             const int row = Q_ROW[e];
             for (int rp = 0; rp < np; ++rp) {
               const double v = f * p.theta_p[(inst * p.P + p0 + rp) * NT + q];
@@ -2339,7 +2455,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         for (int i = sl; i < NRED; i += SUB)
           for (int rp = 0; rp < np; ++rp) {
             double r = sol[rp * NRED + i];
-            for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF[e] * opval(R_CODE[e], jv, th) * wq[rp * NY + R_K[e]];
+            for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF_AT(e) * opval(R_CODE[e], jv, th) * wq[rp * NY + R_K[e]];
             sol[rp * NRED + i] = r;
           }
         __syncwarp(smask);
@@ -2353,7 +2469,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
           for (int c = sl; c < NRED; c += SUB) zp[PERM[c]] = so[c];
           for (int k = sl; k < NY; k += SUB) {
             double hx = 0.0;
-            for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * so[H_COL[e]];
+            for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * so[H_COL[e]];
             const double zy = wq[rp * NY + k] - dinv[k] * hx;
             zp[NX + k] = zy;
             zp[NX + NY + k] = -s[k] * zy / y[k];
@@ -2378,7 +2494,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
       for (int rq = 0; rq < nq; ++rq) {
         const int q = q0 + rq;
         for (int e = Q_PTR[q] + sl; e < Q_PTR[q + 1]; e += SUB) {
-          const double v = -Q_COEF[e] * opval(Q_CODE[e], jtv, th);
+          const double v = -Q_COEF_AT(e) * opval(Q_CODE[e], jtv, th);
           const int row = Q_ROW[e];
           if (row < NX) sol[rq * NRED + IPERM[row]] = v;
           else wq[rq * NY + (row - NX)] = dinv[row - NX] * v;
@@ -2389,7 +2505,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         for (int rq = 0; rq < nq; ++rq) {
           double r = sol[rq * NRED + i];
           for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e)
-            r -= R_COEF[e] * opval(R_CODE[e], jv, th) * wq[rq * NY + R_K[e]];
+            r -= R_COEF_AT(e) * opval(R_CODE[e], jv, th) * wq[rq * NY + R_K[e]];
           sol[rq * NRED + i] = r;
         }
       }
@@ -2414,7 +2530,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         }
         for (int k = sl; k < NY; k += SUB) {
           double hx = 0.0;
-          for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF[e] * opval(H_CODE[e], jv, th) * so[H_COL[e]];
+          for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * so[H_COL[e]];
           const double zy = wq[rq * NY + k] - dinv[k] * hx;
           const double zs = -s[k] * zy / y[k];
           if (p.dzdtheta) {

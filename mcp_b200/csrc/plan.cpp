@@ -252,17 +252,72 @@ std::string dlit(double v) {
   return s;
 }
 
+// Tables are emitted in the narrowest type that holds them: every index table of the reference's configs fits 16 bits
+// and almost every coefficient table is exactly representable in float (±1, small integers) or draws on a handful of
+// distinct doubles (a dictionary).  Why: all warps of an SM walk the same ~45 KB of int/double tables once per Newton step
+// while only ~28 KB of L1 is left beside the shared memory — packed they are ~19 KB and stay L1-resident (ncu r1g/r2a:
+// L1 hit rate 28 %, 22 % of all stall samples were long-scoreboard waits on these loads).
+// MCPB200_WIDE_TABLES=1 restores plain int / double tables.
+bool wide_tables() {
+  const char* e = getenv("MCPB200_WIDE_TABLES");
+  return e && atoi(e) != 0;
+}
+
 template <class T>
-void emit_table(std::ostringstream& os, const char* type, const char* name, const std::vector<T>& v, bool is_double = false) {
+void emit_raw_table(std::ostringstream& os, const char* type, const std::string& name, const std::vector<T>& v, bool is_double = false,
+                    bool is_float = false) {
   os << "__device__ const " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
   if (v.empty()) os << "0";
   for (size_t i = 0; i < v.size(); ++i) {
     if (i) os << ",";
     if (i % 16 == 15) os << "\n";
-    if (is_double) os << dlit((double)v[i]);
+    if (is_float) os << dlit((double)v[i]) << "f";
+    else if (is_double) os << dlit((double)v[i]);
     else os << (long long)v[i];
   }
   os << "};\n";
+}
+
+// `type` "int": narrowed to short when every value fits; "int!" keeps int (tables whose address is taken in the kernels).
+// `type` "double": float / dictionary / double, always read through the generated accessor NAME_AT(i).
+template <class T>
+void emit_table(std::ostringstream& os, const char* type, const char* name, const std::vector<T>& v, bool is_double = false) {
+  const std::string ty(type);
+  if (!is_double) {
+    bool narrow = ty == "int" && !wide_tables();
+    for (size_t i = 0; i < v.size() && narrow; ++i) narrow = (long long)v[i] >= -32768 && (long long)v[i] <= 32767;
+    emit_raw_table(os, narrow ? "short" : (ty == "int!" ? "int" : type), name, v);
+    return;
+  }
+  const std::string nm(name);
+  bool all_float = !wide_tables(), finite = true;
+  std::map<unsigned long long, int> dict;
+  std::vector<double> vals;
+  std::vector<int32_t> idx(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    const double d = (double)v[i];
+    if (!std::isfinite(d)) finite = false;
+    if (!((double)(float)d == d)) all_float = false;
+    unsigned long long bits;
+    memcpy(&bits, &d, 8);
+    auto it = dict.find(bits);
+    if (it == dict.end()) {
+      it = dict.emplace(bits, (int)vals.size()).first;
+      vals.push_back(d);
+    }
+    idx[i] = it->second;
+  }
+  if (all_float && finite) {
+    emit_raw_table(os, "float", nm, v, true, true);
+    os << "#define " << nm << "_AT(i) ((double)" << nm << "[i])\n";
+  } else if (!wide_tables() && vals.size() <= 256 && v.size() > 64) {
+    emit_raw_table(os, "unsigned char", nm + "_IDX", idx);
+    emit_raw_table(os, "double", nm + "_VAL", vals, true);
+    os << "#define " << nm << "_AT(i) (" << nm << "_VAL[" << nm << "_IDX[i]])\n";
+  } else {
+    emit_raw_table(os, "double", nm, v, true);
+    os << "#define " << nm << "_AT(i) (" << nm << "[i])\n";
+  }
 }
 
 struct Emitter {
@@ -1047,12 +1102,19 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   // widest register-window part (entries of one window row held by one lane); MCPB200_REGWIN_PW overrides
   int regwin_pw_max = 40;
   if (const char* e = getenv("MCPB200_REGWIN_PW")) regwin_pw_max = std::max(2, atoi(e));
+  // Geometry of the register-resident window — mirrors BS_NPART / BS_PW / BS_REGWIN of kernel_template.cuh: WR + 1 row
+  // slots (one spare, so the entering row is staged a step early), NPART lanes per row, PW positions per lane covering
+  // WC + 1 relative columns.
+  auto regwin_geom = [&](int& npart, int& pw) -> bool {
+    const int rs = P.R + 1;
+    npart = (rs <= P.sub) ? ((P.sub / rs) >= 4 ? 4 : ((P.sub / rs) >= 2 ? 2 : 1)) : 1;
+    pw = (((P.WC + 1 + npart - 1) / npart) + 1) & ~1;
+    return P.regwin && rs <= P.sub && pw <= regwin_pw_max;
+  };
   auto window_doubles = [&](int ws, int nrhs) -> int64_t {
-    // mirrors the constexpr arithmetic of band_solve (kernel_template.cuh)
-    const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
-    const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
+    int npart, pw;
+    const bool regwin = regwin_geom(npart, pw);
     const int es = (pw * npart + nrhs + 3) & ~1;
-    const bool regwin = P.regwin && P.R <= P.sub && pw <= regwin_pw_max;
     if (!regwin) return (int64_t)P.R * ws + even(P.R) + 4;                 // + mailbox of the cooperative sweep (NWIDE)
     int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
     w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
@@ -1169,9 +1231,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   // the instance's other phases stay on its leader warp.  MCPB200_NWIDE overrides.
   P.nwide = 1;
   if (!P.dense_kernel && P.sub == 32 && P.ipc_solve >= 1 && P.theta_in_smem) {
-    const int npart = (P.R <= P.sub) ? ((P.sub / P.R) >= 4 ? 4 : ((P.sub / P.R) >= 2 ? 2 : 1)) : 1;
-    const int pw = (((P.WC + npart - 1) / npart) + 1) & ~1;
-    const bool regwin_used = P.regwin && P.R <= P.sub && pw <= regwin_pw_max;
+    int npart, pw;
+    const bool regwin_used = regwin_geom(npart, pw);
     const int np = (P.WC + 1 + 1) / 2, pb = std::min(np, 9), nbatch = (np + pb - 1) / pb;
     if (!regwin_used && !P.dense_schur) {
       P.nwide = std::max(1, std::min({4, 16 / P.ipc_solve, nbatch}));
@@ -1374,14 +1435,18 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   os << lay.str();
   {
     std::vector<int32_t> tp(P.d_tptr.size()), rowptr(N + 1, 0);
+    // D_TP: first term of each dest; the sign bit marks a diagonal dest (gets tol).  16-bit when the term count allows.
+    const bool tp16 = !wide_tables() && !P.d_tptr.empty() && P.d_tptr.back() < 32768;
+    os << "#define D_TP_MASK " << (tp16 ? "0x7fff" : "0x7fffffff") << "\n";
     for (size_t i = 0; i < P.d_tptr.size(); ++i)
-      tp[i] = P.d_tptr[i] | ((i < P.d_diag.size() && P.d_diag[i]) ? (int32_t)0x80000000 : 0);
+      tp[i] = tp16 ? (int32_t)(int16_t)(uint16_t)(P.d_tptr[i] | ((i < P.d_diag.size() && P.d_diag[i]) ? 0x8000 : 0))
+                   : (P.d_tptr[i] | ((i < P.d_diag.size() && P.d_diag[i]) ? (int32_t)0x80000000 : 0));
     for (size_t i = 0; i < P.d_row.size(); ++i) rowptr[P.d_row[i] + 1]++;   // dests are sorted by row
     for (int i = 0; i < N; ++i) rowptr[i + 1] += rowptr[i];
     emit_table(os, "int", "D_ROWPTR", rowptr);
     if (P.dense_kernel) emit_table(os, "int", "D_ROW", P.d_row);
     emit_table(os, "int", "D_CPOS", P.d_cpos);
-    emit_table(os, "int", "D_TP", tp);
+    emit_table(os, tp16 ? "int" : "int!", "D_TP", tp);
     emit_table(os, "double", "D_BASE", P.d_base, true);
     // Adjoint sensitivities (θ̄ from z̄ with ONE solve of Cᵀ instead of nθ solves of C): the same non-zeros in
     // column-major order — first dest of each column, window position of its row, index into Cval.
@@ -1404,12 +1469,16 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       for (int i = 0; i < N; ++i) tptr[i + 1] += tptr[i];
       emit_table(os, "int", "DT_ROWPTR", tptr);
       emit_table(os, "int", "DT_CPOS", tcpos);
-      emit_table(os, "int", "DT_SRC", tsrc);
+      emit_table(os, "int!", "DT_SRC", tsrc);
     }
   }
   emit_table(os, "double", "T_COEF", P.t_coef, true);
   {
-    os << "__device__ const int4 T_I[" << std::max<size_t>(P.t_a.size(), 1) << "] = {";
+    bool ti16 = !wide_tables();
+    for (size_t i = 0; i < P.t_a.size() && ti16; ++i)
+      ti16 = std::abs(P.t_a[i]) < 32767 && std::abs(P.t_b[i]) < 32767 && std::abs(P.t_k[i]) < 32767;
+    os << "typedef " << (ti16 ? "short4" : "int4") << " TI_T;\n";
+    os << "__device__ const TI_T T_I[" << std::max<size_t>(P.t_a.size(), 1) << "] = {";
     if (P.t_a.empty()) os << "{0,0,0,0}";
     for (size_t i = 0; i < P.t_a.size(); ++i) {
       if (i) os << ",";

@@ -20,6 +20,28 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if len(b) else 0.0
 
 
+_EXT = {}
+
+
+def rounding_sensitive(mcp, θ, x_ref, tol, x0=None, y0=None, **kw):
+    """True when the FP64 oracle's own result for this instance is farther than a tenth of the parity bar from the
+    extended-precision trajectory (`oracle/ip_oracle_ext.py`): the trajectory then hinges on rounding and no FP64
+    implementation can be held to 1e-6 on it (measured records in profiles/r2_adjudicate_*.json)."""
+    from oracle import ip_oracle_ext as E
+    key = id(mcp.ir)
+    if key not in _EXT:
+        _EXT[key] = OracleMCP(mcp.ir, extended=True)
+    e = E.solve_interior_point_ext(_EXT[key], θ, x0=x0, y0=y0, tol=tol, **kw)
+    return e.status != "solved" or rel_err(np.asarray(x_ref), e.x.astype(np.float64)) > 0.1 * RTOL
+
+
+def golden_ill_conditioned(name):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ill_conditioned.json")) as f:
+        return {int(k) for k in json.load(f)[name]}
+
+
 def compare_batch(mcp, Θ, sol, tol, x0=None, y0=None, min_match=1.0, **kw):
     om = OracleMCP(mcp.ir)
     B = Θ.shape[1]
@@ -83,7 +105,7 @@ def test_lane_change_batch(lane_game):
     mcp = lane_game.mcp
     Θ = problems.lane_change_thetas(48, seed=1)
     sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
-    frac, worst = compare_batch(mcp, Θ, sol, tol=1e-6, min_match=0.95)
+    frac, worst = compare_batch(mcp, Θ, sol, tol=1e-6, min_match=1.0)     # measured: 48/48
     print(f"lane-change parity: {frac:.3f} matched, worst rel err {worst:.2e}")
 
 
@@ -92,7 +114,7 @@ def test_lane_change_warm_start(lane_game):
     Θ = problems.lane_change_thetas(16, seed=3)
     x0 = problems.lane_change_zero_input_x0(Θ)
     sol = solve(InteriorPoint(), mcp, Θ, x0=x0, tol=1e-4)
-    compare_batch(mcp, Θ, sol, tol=1e-4, x0=x0, min_match=0.9)
+    compare_batch(mcp, Θ, sol, tol=1e-4, x0=x0, min_match=1.0)
 
 
 def test_sensitivities_readme(readme_mcp):
@@ -388,7 +410,7 @@ def test_large_batch_properties(lane_game):
             agree += 1
         elif ref.status[k] == 1 and sol.status[b] == 1:
             agree += 1
-    assert agree >= 62
+    assert agree == 64
 
 
 # ---- cfg4: masked N-player game (examples/train_and_test_utils.jl:362-401), N = 4, horizon 30 ------------------
@@ -466,10 +488,11 @@ def test_masked_game_jacobian_consistency():
 
 
 def test_lane_change_parity_statistics(lane_game):
-    """1 024 random lane-change instances against the C oracle: how often does the GPU follow the oracle's
-    trajectory to the bar (same status, Newton steps within ±1, x/y/s within 1e-6 relative)?  Decisions taken
-    at exact floating-point boundaries (kkt_error vs ϵ, the linesearch predicate) may legitimately flip, so the
-    requirement is ≥ 99 %, and every solved instance must at least reach the same status."""
+    """1 024 random lane-change instances against the C oracle: same status, Newton steps within ±1, x/y/s within
+    1e-6 relative — on EVERY instance (measured on B200: 1 024 / 1 024, identical step counts on all 986 solved ones,
+    GPU within 9.3e-9 and the C oracle within 3.4e-13 of the extended-precision trajectory,
+    profiles/r2_adjudicate_lane_change.json).  An instance may miss the bar only if the FP64 oracle itself is off the
+    extended-precision trajectory (decided at run time) AND it is named in tests/golden/ill_conditioned.json (none is)."""
     from oracle import c_oracle as CO
     mcp = lane_game.mcp
     B = 1024
@@ -489,8 +512,10 @@ def test_lane_change_parity_statistics(lane_game):
     print(f"parity: {ok.sum()}/{B} to the bar, status agreement {same_status.sum()}/{B}, "
           f"identical step counts {int((sol.newton_steps[solved] == ref.newton_steps[solved]).sum())}/{int(solved.sum())}, "
           f"worst rel err among step-matched {worst:.2e}")
-    assert same_status.mean() >= 0.995
-    assert ok.mean() >= 0.99
+    allowed = golden_ill_conditioned("lane_change_seed2024_B1024_tol1e-6")
+    for b in np.nonzero(~ok)[0]:
+        assert int(b) in allowed, f"instance {b} misses the bar and is not a named rounding-sensitive instance"
+        assert rounding_sensitive(mcp, Θ[:, b], ref.x[:, b], 1e-6), f"instance {b}: the FP64 oracle follows the exact trajectory, the GPU does not"
 
 
 def test_masked_game_parity_statistics():
@@ -515,8 +540,15 @@ def test_masked_game_parity_statistics():
             worst = max(worst, e)
     print(f"masked-game parity: {ok.sum()}/{B} to the bar, status agreement {same_status.sum()}/{B}, worst rel err {worst:.2e}")
     assert solved.sum() >= 0.9 * B
-    assert same_status.mean() >= 0.99
-    assert ok.mean() >= 0.98
+    assert same_status.all()
+    # Measured (profiles/r2_adjudicate_masked_n4.json): 253 / 256 to the bar; on the other three — instances 130, 184, 185 —
+    # the FP64 C oracle itself is 6.4e-2 / 4.3e-3 / 1.9e-6 away from the extended-precision trajectory (different
+    # Newton-step counts: 61 vs 63, 70 vs 103 on the first two): their trajectories hinge on rounding.  Exactly those
+    # named instances may miss, and the reason is re-verified here.
+    allowed = golden_ill_conditioned("masked_n4_seed11_B256_tol1e-4")
+    for b in np.nonzero(~ok)[0]:
+        assert int(b) in allowed, f"instance {b} misses the bar and is not a named rounding-sensitive instance"
+        assert rounding_sensitive(mcp, Θ[:, b], ref.x[:, b], 1e-4, x0=x0[:, b]), f"instance {b}: not rounding-sensitive"
 
 
 def test_in_library_multi_device_sharding(lane_game):
@@ -579,6 +611,6 @@ def test_gpu_solutions_satisfy_independent_kkt(lane_game):
         G, Hms, sy = F[:200], F[200:450], F[450:]
         H = Hms + sol.s[:, b]
         assert np.max(np.abs(G)) <= 1e-5 and np.min(H) >= -1e-5 and np.min(sol.y[:, b]) >= 0
-        assert np.max(np.abs(Hms)) <= 1e-5 and np.max(sy) <= 1e-5 and float(sol.y[:, b] @ H) <= 1e-3
+        assert np.max(np.abs(Hms)) <= 1e-5 and np.max(sy) <= 1e-4 and float(sol.y[:, b] @ H) <= 250 * 1e-4
         checked += 1
     assert checked >= 28
