@@ -423,7 +423,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         const double2* up = reinterpret_cast<const double2*>(Pb + part * PW);
 #pragma unroll
         for (int k = 0; k <= PW / 2; ++k) {  // PW/2 + 1 aligned pairs: my part and the first entry of the next
+#ifdef EXP_NO_UBCAST
+          const double2 v = make_double2(1.0 + k, 2.0);
+#else
           const double2 v = up[k];
+#endif
           u[2 * k] = v.x;
           u[2 * k + 1] = v.y;
         }
@@ -458,7 +462,9 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
         const int t = sl + SUB * k;
+#ifndef EXP_NO_UT_STORE
         if (t < WC && t < left) __stcg(UTj + (size_t)k * SUB * (UTS + 1), (t == 0) ? rp : ut_out[k]);
+#endif
       }
       // ---- eliminate column j and slide the window: a[i] ← a[i+1] − m·u[i+1] ------------------------------
 #pragma unroll
@@ -667,84 +673,79 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   // multiply + broadcast by the row's owner and one FMA per accumulator — `sol` is read and written once per row
   // instead of once per (row, column).  The columns of U (rows of UT) stream back through two cp.async buffers of
   // BS_CH rows each that re-use the window's shared memory.
+#ifndef EXP_NO_BACKSUB
   {
-    constexpr int BS_CH = (RING_D >= 2) ? RING_D / 2 : 1;
+    // Each lane needs ONE entry of Uᵀ's row j per accumulator (its own row's coefficient in column j), so the rows of
+    // Uᵀ are read straight from the L2 into registers, a block of BS_BD columns ahead of their use (two register
+    // blocks, ping-pong): ≈ BS_BD·50 cycles of lead cover the L2 latency, nothing goes through shared memory, there
+    // is no barrier inside the sweep.  (r2 measurement, fixed-work mode: the cp.async ring this replaces kept only
+    // 4–8 rows in flight and the sweep ran at ≈400 cycles per column — 19 % of the whole Newton step.)
     constexpr int NACC = (WC - 1) / SUB + 1;
-    constexpr int CHP = BS_CH * UTS / 2;   // 16-byte pieces per chunk
-    double* ring = W;
-    // chunk c holds UT rows [lo, lo + BS_CH) with lo = NRED − (c+1)·BS_CH (clipped at 0: the last chunk is partial)
-    auto issue = [&](int c) {
-      const int hi = NRED - c * BS_CH;   // exclusive
-      if (hi > 0) {
-        const int lo = (hi - BS_CH > 0) ? hi - BS_CH : 0;
-        const double* src = UT + (size_t)lo * UTS;
-        double* dst = ring + (c & 1) * (BS_CH * UTS) + (lo - (hi - BS_CH)) * UTS;
-        const int np = (hi - lo) * UTS / 2;
-#pragma unroll
-        for (int k = 0; k < (CHP + SUB - 1) / SUB; ++k) {
-          const int t2 = sl + SUB * k;
-          if (t2 < np) cp_async16(dst + 2 * t2, src + 2 * t2);
-        }
-      }
-      cp_async_commit();  // (possibly empty) group: keeps the group count uniform
-    };
-    __syncwarp(smask);
-    issue(0);
-    issue(1);
+#ifndef BS_BD_MAX
+#define BS_BD_MAX 12
+#endif
+    constexpr int BS_BD = (BS_BD_MAX / (NACC * NRHS) >= 4) ? BS_BD_MAX / (NACC * NRHS) : 4;
     double acc[NRHS][NACC];
-    int t0 = (((NRED - 1 - sl) % SUB) + SUB) % SUB;   // distance from column j down to my nearest row: row j − t0 is acc[·][0]
+    const int t0s = (((NRED - 1 - sl) % SUB) + SUB) % SUB;   // (column − lane) mod SUB at column NRED − 1
 #pragma unroll
     for (int q = 0; q < NRHS; ++q)
 #pragma unroll
       for (int k = 0; k < NACC; ++k) {
-        const int i = NRED - 1 - t0 - SUB * k;
+        const int i = NRED - 1 - t0s - SUB * k;
         acc[q][k] = (i >= 0) ? sol[q * NRED + i] : 0.0;
       }
-    constexpr int NCHUNK = (NRED + BS_CH - 1) / BS_CH;
-    int own = (NRED - 1) % SUB;   // lane that owns row j
-    // one column: x_j from its owner, then every lane updates the rows it owns inside the dependency window
-    auto column = [&](int j, const double* Uj) {
-      double ut[NACC];
+    // my entries of Uᵀ's rows jhi, jhi − 1, …: row j − t of column j with t = ((j − lane) mod SUB) + SUB·k
+    auto load_block = [&](int jhi, double (&dst)[BS_BD][NACC]) {
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        const int t = t0 + SUB * k;
-        ut[k] = (t < WC) ? Uj[t] : 0.0;   // t == 0: the reciprocal pivot
-      }
+      for (int jj = 0; jj < BS_BD; ++jj) {
+        const int j = jhi - jj;
+        const int t0 = (j - sl) & (SUB - 1);
 #pragma unroll
-      for (int q = 0; q < NRHS; ++q) {
-        const double xj = __shfl_sync(smask, acc[q][0] * ut[0], own, SUB);
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {   // rows j − t, t = t0 + SUB·k ∈ [1, WC)
+        for (int k = 0; k < NACC; ++k) {
           const int t = t0 + SUB * k;
-          if (t >= 1 && t < WC) acc[q][k] = fma(-ut[k], xj, acc[q][k]);
-        }
-        if (t0 == 0 && j >= 0) {   // row j is finished: store it, my accumulators move on to rows j − SUB, j − 2·SUB, …
-          sol[q * NRED + j] = xj;
-#pragma unroll
-          for (int k = 0; k + 1 < NACC; ++k) acc[q][k] = acc[q][k + 1];
-          const int inext = j - SUB * NACC;
-          acc[q][NACC - 1] = (inext >= 0) ? sol[q * NRED + inext] : 0.0;
+          dst[jj][k] = (j >= 0 && t < WC) ? __ldcg(UT + (size_t)j * UTS + t) : 0.0;   // t == 0: the reciprocal pivot
         }
       }
-      t0 = (t0 + SUB - 1) % SUB;
-      own = (own + SUB - 1) % SUB;
     };
-#pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
-      cp_async_wait<1>();
-      __syncwarp(smask);
-      const double* buf = ring + (c & 1) * (BS_CH * UTS);
-      const int jhi = NRED - 1 - c * BS_CH;
-      // (the last chunk may run past column 0: those virtual columns only touch accumulators of rows that do not
-      // exist and stale ring data; keeping the control flow uniform keeps the shuffles free of re-convergence code)
+    // columns jhi … jhi − BS_BD + 1: x_j from its owner (lane j mod SUB), then every lane updates the rows it owns
+    // inside the dependency window.  Columns below 0 (last block) are virtual: they only touch accumulators of rows
+    // that do not exist; the control flow stays uniform, so the shuffles need no re-convergence code.
+    auto sweep_block = [&](int jhi, const double (&ub)[BS_BD][NACC]) {
 #pragma unroll
-      for (int jj = 0; jj < BS_CH; ++jj) column(jhi - jj, buf + (BS_CH - 1 - jj) * UTS);
-      __syncwarp(smask);      // everyone is done with this buffer before it is refilled
-      issue(c + 2);
+      for (int jj = 0; jj < BS_BD; ++jj) {
+        const int j = jhi - jj;
+        const int t0 = (j - sl) & (SUB - 1);
+#pragma unroll
+        for (int q = 0; q < NRHS; ++q) {
+          const double xj = __shfl_sync(smask, acc[q][0] * ub[jj][0], j & (SUB - 1), SUB);
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) {   // rows j − t, t = t0 + SUB·k ∈ [1, WC)
+            const int t = t0 + SUB * k;
+            if (t >= 1 && t < WC) acc[q][k] = fma(-ub[jj][k], xj, acc[q][k]);
+          }
+          if (t0 == 0 && j >= 0) {   // row j is finished: store it, my accumulators move on to rows j − SUB, j − 2·SUB, …
+            sol[q * NRED + j] = xj;
+#pragma unroll
+            for (int k = 0; k + 1 < NACC; ++k) acc[q][k] = acc[q][k + 1];
+            const int inext = j - SUB * NACC;
+            acc[q][NACC - 1] = (inext >= 0) ? sol[q * NRED + inext] : 0.0;
+          }
+        }
+      }
+    };
+    __syncwarp(smask);   // the factorisation's stores to UT / sol (other lanes) are visible from here
+    double ua[BS_BD][NACC], ub[BS_BD][NACC];
+    load_block(NRED - 1, ua);
+#pragma unroll 1
+    for (int jhi = NRED - 1; jhi >= 0; jhi -= 2 * BS_BD) {
+      load_block(jhi - BS_BD, ub);
+      sweep_block(jhi, ua);
+      load_block(jhi - 2 * BS_BD, ua);
+      sweep_block(jhi - BS_BD, ub);
     }
-    cp_async_wait<0>();
     __syncwarp(smask);
   }
+#endif
   return 0;
 }
 
@@ -2164,7 +2165,11 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
         brk = false;
       }
       if (head) {  // top of the outer (ϵ-homotopy) loop, :71
+#ifdef EXP_FIXED_STEPS   // timing experiments (MCPB200_DEFS): exactly EXP_FIXED_STEPS identical Newton steps per instance
+        const bool go = steps < EXP_FIXED_STEPS;
+#else
         const bool go = kkt > tol && eps > tol && outer < p.max_outer;
+#endif
         const bool park = go && p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget;
         if (!go || park) {
           if (!park && outer == p.max_outer) status = 1;  // :117-119
@@ -2194,7 +2199,11 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
         status = 0;  // :73
         head = false;
       }
+#ifdef EXP_FIXED_STEPS
+      if (steps < EXP_FIXED_STEPS) {
+#else
       if (!brk && kkt > eps && inner < p.max_inner) {  // :75
+#endif
         step = true;
       } else {  // the inner loop is over: ϵ update, :111-114
         eps *= (status == 0) ? 1.0 - exp(-p.tightening_rate * inner) : 1.0 + exp(-p.loosening_rate * inner);
@@ -2214,7 +2223,9 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     mcp_eval_newton_par(sl, x, y, th, g, hh, jv);
     wide_bar(1 + slot, NWIDE * 32);
 #else
+#ifndef EXP_NO_EVAL
     mcp_eval_newton_par(sl, x, y, th, g, hh, jv);
+#endif
     __syncwarp(smask);
 #endif
     double fmax_ = 0.0;
@@ -2246,10 +2257,16 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     wide_bar(1 + slot, NWIDE * 32);
     assemble_matrix<NWIDE>(Cval, W, jv, th, dinv, tol, sl, smask, 0, 1 + slot);
 #else
+#ifndef EXP_NO_ASM
     assemble_matrix(Cval, W, jv, th, dinv, tol, sl, smask);
+#endif
     __syncwarp(smask);
 #endif
+#ifdef EXP_NO_LU
+    bool failed = false;
+#else
     bool failed = band_solve<1, WS1, NWIDE>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + SOLVE_OFF_STAGE, sl, smask, 1 + slot) != 0;  // :84-88
+#endif
     double a_s = 1.0, a_y = 1.0;
     if (!failed) {
       // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
@@ -2267,11 +2284,22 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
       a_y = ftb_linesearch(y, w, p.min_stepsize, sl, smask);     // :94
       failed = (a_s != a_s) || (a_y != a_y);                     // :96-100
     }
+#ifdef EXP_FIXED_STEPS
+    failed = false;   // the iterate stays where it is: every step does the same work
+    a_s = 0.0;
+    a_y = 0.0;
+#endif
     if (failed) {
       status = 1;
       brk = true;
     } else {
+#ifdef EXP_FIXED_STEPS
+      if (a_s != 0.0)
+#endif
       for (int c = sl; c < NRED; c += SUB) x[PERM[c]] += a_s * sol[c];  // :103 (x uses α_s)
+#ifdef EXP_FIXED_STEPS
+      if (a_s != 0.0)
+#endif
       for (int k = sl; k < NY; k += SUB) {
         s[k] += a_s * dinv[k];                                          // :104
         y[k] += a_y * w[k];                                             // :105
