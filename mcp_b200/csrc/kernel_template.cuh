@@ -123,6 +123,7 @@ __device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, F
 #define BS_REGWIN (REGWIN && BS_RS <= SUB && BS_PW <= REGWIN_PW_MAX)
 #define BS_PREFETCH_AT ((NRED > 8) ? 8 : 1)   // pivot steps before the end of the factorisation at which Uᵀ is prefetched into the L2
 
+template <int NRHS = 1>
 __device__ __forceinline__ void load_shared_tables(double* smem_base, bool transposed = false) {
   int* rowptr = reinterpret_cast<int*>(smem_base);
   unsigned short* cpos = reinterpret_cast<unsigned short*>(rowptr + NRED + 1);
@@ -307,6 +308,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
   constexpr int PW = BS_PW;
   constexpr int WCP = PW * NPART;               // padded matrix width (≥ WC + 1)
   constexpr int ES = (WCP + NRHS + 3) & ~1;     // stride of the publish / staging rows (even, one pair of slack)
+  // (r2 experiment, removed: a COLUMN-owner register window — lane ℓ owns window column ≡ ℓ mod WC with all WR row slots
+  // in registers, pivot search local to one lane, multipliers broadcast by shuffle, no pivot-row publish / reload — cut the
+  // shared-memory + shuffle operations per pivot step from ≈62 to ≈35 but needs ≈186 instead of ≈134 issued instructions
+  // per step (local search, two uniform switches on the pivot slot, per-slot multiplier shuffles); measured in the
+  // fixed-work mode 178.3 vs 167.7 ms: the step is bound by the warp's serial instruction latency, not by the MIO pipe.)
   if constexpr (BS_REGWIN) {
     // ============ register-resident window ==========================================================
     // Window rows live in REGISTERS for their whole life in the window, each row split over NPART lanes:
@@ -682,7 +688,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     // 4–8 rows in flight and the sweep ran at ≈400 cycles per column — 19 % of the whole Newton step.)
     constexpr int NACC = (WC - 1) / SUB + 1;
 #ifndef BS_BD_MAX
-#define BS_BD_MAX 12
+#define BS_BD_MAX 8
 #endif
     constexpr int BS_BD = (BS_BD_MAX / (NACC * NRHS) >= 4) ? BS_BD_MAX / (NACC * NRHS) : 4;
     double acc[NRHS][NACC];
@@ -2027,7 +2033,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
   const int slot = threadIdx.x / SUB;  // instance slot of this sub-warp within the CTA
 #endif
   const unsigned smask = sub_mask(threadIdx.x & 31);
-  load_shared_tables(smem);
+  load_shared_tables<1>(smem);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
   double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SOLVE_SMEM_DOUBLES;  // my shared-memory block
@@ -2367,7 +2373,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
   // forward solves (mcp_sens_kernel).
   constexpr bool adjoint = L::ADJ;
   constexpr int NRHS_L = L::NRHS;
-  load_shared_tables(smem, adjoint);
+  load_shared_tables<NRHS_L>(smem, adjoint);
   const int* rowptr = reinterpret_cast<const int*>(smem);
   const unsigned short* cpos = reinterpret_cast<const unsigned short*>(rowptr + NRED + 1);
   double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * L::SMEM;
