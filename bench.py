@@ -172,6 +172,225 @@ def run_reference(args):
     return 0
 
 
+def _time_device(fn, stream, reps: int):
+    """CUDA-event time (ms) of `reps` calls of fn on torch's current stream, after one warm-up call."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def other_workloads(local: int, fp64_peak: float, hbm_gbs: float, reps: int = 3):
+    """The other four BASELINE.json configs, timed in the same run (N = 1 only) at small repetition counts:
+    cfg1 README QP 2^20 θ, cfg2 random QP 100×100 cold + the warm-started θ sweep
+    (benchmark/quadratic_program_benchmark.jl:51-74), cfg5 lane-change VJP + full Jacobian, cfg4 masked game N = 4.
+    Each entry: converged solves/s device-resident (`value`), kernel_ms, the roofline fraction of its solve kernel, and
+    the end-to-end figure through the host C-ABI call where the workload has one."""
+    import torch
+    from mcp_b200 import capi, problems, torch_api
+    from mcp_b200.solver import _handle
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def solve_entry(mcp, Θ_host, tol, x0=None, y0=None, e2e=True, note=None):
+        h = _handle(mcp)
+        nx, ny, nt = mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension
+        B = Θ_host.shape[1]
+        θp = torch.from_numpy(np.ascontiguousarray(Θ_host.T)).pin_memory()
+        θd = θp.to(dev)
+        sol = dict(x=torch.empty((B, nx), dtype=torch.float64, device=dev), y=torch.empty((B, ny), dtype=torch.float64, device=dev),
+                   s=torch.empty((B, ny), dtype=torch.float64, device=dev), kkt=torch.empty(B, dtype=torch.float64, device=dev),
+                   eps=torch.empty(B, dtype=torch.float64, device=dev), outer=torch.empty(B, dtype=torch.int32, device=dev),
+                   status=torch.empty(B, dtype=torch.int32, device=dev), steps=torch.empty(B, dtype=torch.int32, device=dev))
+        dopts = capi.default_opts(tol=tol)
+
+        def step():   # the device entry point on resident tensors, outputs allocated once (as in the headline loop)
+            h.check(h._lib.mcpb200_solve_batched_device(
+                h.raw, B, θd.data_ptr(), None if x0 is None else x0.data_ptr(), None if y0 is None else y0.data_ptr(), None,
+                C.byref(dopts), sol["x"].data_ptr(), sol["y"].data_ptr(), sol["s"].data_ptr(), sol["kkt"].data_ptr(),
+                sol["eps"].data_ptr(), sol["outer"].data_ptr(), sol["status"].data_ptr(), sol["steps"].data_ptr(),
+                C.c_void_p(stream.cuda_stream)))
+        ms = _time_device(step, stream, reps)
+        tm, info = h.timing(), h.info()
+        solved = int(tm["solved"])
+        flops = info["flops_per_newton_step_band"] * tm["newton_steps"]
+        io_bytes = B * (8 * (nt + nx + 2 * ny) + 24)
+        ent = {"batch": B, "tol": tol, "value": solved / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+               "kernel_ms": tm["kernel_ms"], "kernel_only_value": solved / (tm["kernel_ms"] * 1e-3), "solved_fraction": solved / B, "newton_steps": int(tm["newton_steps"]),
+               "roofline": {"bound": "fp64", "achieved": flops / (tm["kernel_ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": flops / (tm["kernel_ms"] * 1e-3) / 1e12 / fp64_peak,
+                            "flops_per_newton_step": info["flops_per_newton_step_band"]},
+               "hbm_io": {"achieved": io_bytes / (tm["kernel_ms"] * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                          "frac": io_bytes / (tm["kernel_ms"] * 1e-3) / 1e9 / hbm_gbs}}
+        if note:
+            ent["note"] = note
+        if e2e:
+            host = [torch.empty((B, n), dtype=torch.float64).pin_memory() for n in (nx, ny, ny)]
+            hk, he = torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory()
+            ho, hs, hn = (torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(3))
+            opts = capi.default_opts(tol=tol)
+            h.set_devices([local])
+
+            def host_step():
+                h.check(h._lib.mcpb200_solve_batched(h.raw, B, θp.data_ptr(), None, None, None, C.byref(opts), host[0].data_ptr(),
+                                                     host[1].data_ptr(), host[2].data_ptr(), hk.data_ptr(), he.data_ptr(),
+                                                     ho.data_ptr(), hs.data_ptr(), hn.data_ptr()))
+            host_step()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                host_step()
+            dt = (time.perf_counter() - t0) / reps
+            ent["e2e"] = {"value": int((hs == 0).sum()) / dt, "unit": UNIT, "h2d_bytes_per_step": B * nt * 8,
+                          "d2h_bytes_per_step": B * ((nx + 2 * ny) * 8 + 28), "ms_per_step": dt * 1e3}
+        return ent, sol, θd
+
+    # cfg1 — README QP, 2^20 θ, defaults (tol 1e-4) and tol 1e-6
+    mcp = problems.readme_qp()
+    Θ = problems.readme_qp_thetas(1 << 20, seed=1)
+    out["cfg1_readme_qp_tol1e-4"], _, _ = solve_entry(mcp, Θ, 1e-4)
+    out["cfg1_readme_qp_tol1e-6"], _, _ = solve_entry(mcp, Θ, 1e-6, e2e=False)
+    # cfg2 — random convex QP 100×100: cold, then the θ sweep (ϕ ← ϕ + 0.01·N(0,1)) warm-started from the cold solution
+    mcp = problems.random_qp(100, 100)
+    Bq = 1 << 13
+    Θ = problems.random_qp_thetas(Bq, seed=1)
+    cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1")
+    out["cfg2_random_qp_cold"] = cold
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    θ2 = θd.clone()
+    θ2[:, -100:] += 0.01 * torch.randn((Bq, 100), dtype=torch.float64, device=dev, generator=g)
+    x0, y0 = sol["x"].clone(), sol["y"].clamp_min(1e-3)
+    h = _handle(mcp)
+    warm = {k: torch.empty_like(v) for k, v in sol.items()}
+    dopts = capi.default_opts(tol=TOL)
+
+    def warm_step():
+        h.check(h._lib.mcpb200_solve_batched_device(
+            h.raw, Bq, θ2.data_ptr(), x0.data_ptr(), y0.data_ptr(), None, C.byref(dopts), warm["x"].data_ptr(), warm["y"].data_ptr(),
+            warm["s"].data_ptr(), warm["kkt"].data_ptr(), warm["eps"].data_ptr(), warm["outer"].data_ptr(), warm["status"].data_ptr(),
+            warm["steps"].data_ptr(), C.c_void_p(stream.cuda_stream)))
+    ms = _time_device(warm_step, stream, reps)
+    tm, info = h.timing(), h.info()
+    flops = info["flops_per_newton_step_band"] * tm["newton_steps"]
+    out["cfg2_random_qp_warm_sweep"] = {
+        "batch": Bq, "tol": TOL, "value": int(tm["solved"]) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": tm["kernel_ms"],
+        "solved_fraction": int(tm["solved"]) / Bq, "newton_steps": int(tm["newton_steps"]),
+        "newton_steps_cold": cold["newton_steps"],
+        "roofline": {"bound": "fp64", "achieved": flops / (tm["kernel_ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": flops / (tm["kernel_ms"] * 1e-3) / 1e12 / fp64_peak},
+        "note": "same M, A, b; ϕ perturbed by 0.01·N(0,1); x₀, y₀ = cold solution (y₀ clamped ≥ 1e-3), s₀ = 1, ϵ restarts at 1 "
+                "(src/solver.jl:41,67)"}
+    del θd, θ2, sol, warm, x0, y0
+    torch.cuda.empty_cache()
+    # cfg5 — lane-change sensitivities: VJP (adjoint kernel) and the full Jacobian ∂z/∂θ (10 right-hand sides)
+    mcp = problems.lane_change_game().mcp
+    h = _handle(mcp)
+    nx, ny, nt = mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension
+    Bs = 1 << 14
+    θd = torch.from_numpy(np.ascontiguousarray(problems.lane_change_thetas(Bs, seed=5, moving=True).T)).to(dev)
+    sol = torch_api.solve_device(mcp, θd, tol=TOL)
+    zbar = torch.cat([2 * sol["x"], 2 * sol["y"], torch.zeros_like(sol["s"])], dim=1).contiguous()
+    ms = _time_device(lambda: torch_api.pullback_device(mcp, θd, sol["x"], sol["y"], sol["s"], sol["eps"], zbar), stream, reps)
+    tm = h.timing()
+    out["cfg5_lane_change_vjp"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "VJPs/s", "ms_per_step": ms,
+                                   "kernel_ms": tm["kernel_ms"], "note": "adjoint mode: one solve with Cᵀ per instance (src/AutoDiff.jl:59-76)"}
+    jac = torch.empty((Bs, nt, nx + 2 * ny), dtype=torch.float64, device=dev)
+
+    def jac_step():
+        h.check(h._lib.mcpb200_sensitivities_device(h.raw, Bs, θd.data_ptr(), sol["x"].data_ptr(), sol["y"].data_ptr(), sol["s"].data_ptr(),
+                                                    sol["eps"].data_ptr(), jac.data_ptr(), None, None, 0, None, None, None,
+                                                    C.c_void_p(stream.cuda_stream)))
+    ms = _time_device(jac_step, stream, reps)
+    tm = h.timing()
+    out["cfg5_lane_change_jacobian"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "Jacobians/s", "ms_per_step": ms,
+                                        "kernel_ms": tm["kernel_ms"], "note": "∂z/∂θ, 700×10 per instance (src/AutoDiff.jl:18-40)"}
+    del jac, zbar, sol, θd
+    torch.cuda.empty_cache()
+    # cfg4 — masked game N = 4, H = 30: all 8 ego masks × 256 scenarios, stay-at-rest x₀, tol 1e-4 (the application's settings)
+    mcp = problems.masked_game(4, 30).mcp
+    Θ = problems.masked_game_thetas(8192, 4, seed=1)
+    x0 = torch.from_numpy(np.ascontiguousarray(problems.masked_game_x0(Θ, 4, 30).T)).to(dev)
+    out["cfg4_masked_game_n4"], _, _ = solve_entry(mcp, Θ, 1e-4, x0=x0, e2e=False, note="8 ego masks × 1024 scenarios, x₀ = stay-at-rest rollout")
+    return out
+
+
+def measured_traffic(workload: str):
+    """DRAM bytes per Newton step of the solve kernel, from the committed one-launch ncu capture that carries its OWN step
+    count (`profiles/r2_traffic.json`: fixed-work mode, B × 30 Newton steps in the captured launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
+def run_single_process(args):
+    """`--single-process --gpus N`: ONE process, ONE `mcpb200_solve_batched` call per step after
+    `mcpb200_set_devices(0..N-1)` — north_star's "θ batch sharded across the GPUs of one box, gathered on the host" as a
+    single plugin call (one host thread per device inside the library, no collective).  Host arrays are plain PAGEABLE
+    numpy arrays, as a Julia caller's would be (the library page-locks them for the duration of the call); the same
+    call on pinned arrays is timed next to it."""
+    import torch
+    from mcp_b200 import capi
+    from mcp_b200.solver import _handle
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit(f"--single-process --gpus {N}: only {torch.cuda.device_count()} GPUs visible")
+    mcp, gen, desc = build_workload(args.workload)
+    h = _handle(mcp)
+    lib = h._lib
+    nx, ny, nt = mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension
+    B = args.batch * N
+    W, K = max(args.warmup, 1), args.steps
+    Θ = np.ascontiguousarray(gen(B, 1).T)                       # [B, nθ] row-major = column-major nθ×B, pageable
+    opts = capi.default_opts(tol=TOL)
+    h.set_devices(list(range(N)))
+
+    def buffers(pinned):
+        def mk(shape, dt):
+            a = torch.empty(shape, dtype=dt)
+            return a.pin_memory() if pinned else a
+        θ = torch.from_numpy(Θ)
+        return dict(θ=θ.pin_memory() if pinned else θ, x=mk((B, nx), torch.float64), y=mk((B, ny), torch.float64),
+                    s=mk((B, ny), torch.float64), kkt=mk(B, torch.float64), eps=mk(B, torch.float64),
+                    outer=mk(B, torch.int32), status=mk(B, torch.int32), steps=mk(B, torch.int32))
+
+    def timed(buf):
+        def step():
+            h.check(lib.mcpb200_solve_batched(h.raw, B, buf["θ"].data_ptr(), None, None, None, C.byref(opts), buf["x"].data_ptr(),
+                                              buf["y"].data_ptr(), buf["s"].data_ptr(), buf["kkt"].data_ptr(), buf["eps"].data_ptr(),
+                                              buf["outer"].data_ptr(), buf["status"].data_ptr(), buf["steps"].data_ptr()))
+            return int((buf["status"] == 0).sum())
+        for _ in range(W):
+            step()
+        t0 = time.perf_counter()
+        solved = sum(step() for _ in range(K))
+        dt = time.perf_counter() - t0
+        return solved / dt, dt / K * 1e3, h.timing()
+
+    with ClockSampler(0) as clocks:
+        v_page, ms_page, tm = timed(buffers(False))
+    v_pin, ms_pin, _ = timed(buffers(True))
+    line = {"metric": METRIC, "value": tm["solved"] / (tm["kernel_ms"] * 1e-3), "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": ms_page, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "mode": "single-process: one mcpb200_solve_batched call over all GPUs (mcpb200_set_devices)",
+                       "batch_per_gpu": args.batch, "global_batch": B, "tol": TOL, "launches_per_call": int(tm["launches"]),
+                       "value_is": "converged solves ÷ the slowest device's kernel time (library CUDA events)"},
+            "e2e": {"value": v_page, "unit": UNIT, "ms_per_step": ms_page, "host_memory": "pageable (page-locked per call by the library)",
+                    "h2d_bytes_per_step": B * nt * 8, "d2h_bytes_per_step": B * ((nx + 2 * ny) * 8 + 28)},
+            "e2e_pinned": {"value": v_pin, "unit": UNIT, "ms_per_step": ms_pin},
+            "gpu_launches": K * int(tm["launches"]), "clocks": clocks.summary()}
+    _emit(line)
+    return 0
+
+
 _RESULT_FD = None
 
 
@@ -205,12 +424,17 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="θ columns per GPU per step (default per workload)")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--ref-sample", type=int, default=2048)
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process, one mcpb200_solve_batched call spanning --gpus devices (not the driver's torchrun contract)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the cfg1/2/4/5 entries (N = 1 only)")
     args = ap.parse_args()
     if args.batch is None:   # lane-change: 2^18 (tail of never-converging instances amortised); QP: θ is 161 KB/instance
         args.batch = {"lane_change": 1 << 18, "readme_qp": 1 << 20, "random_qp": 1 << 15}.get(args.workload, 1 << 16)
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process:
+        return run_single_process(args)
 
     import torch
     import torch.distributed as dist
@@ -313,14 +537,10 @@ def main():
         flops_per_launch = info["flops_per_newton_step_band"] * tm["newton_steps"]
         achieved_tf = flops_per_launch / (tm["kernel_ms"] * 1e-3) / 1e12
         io_bytes = B * (8 * (nt + nx + 2 * ny) + 24)
-        traffic = None   # DRAM bytes of the solve launch: per-Newton-step figure from the committed ncu capture
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                per_step = json.load(f).get(args.workload, {}).get("dram_bytes_per_newton_step")
-            if per_step:
-                traffic = float(per_step) * tm["newton_steps"]
-        except (OSError, ValueError):
-            pass
+        # DRAM bytes of the solve launches of one step: the per-Newton-step figure of the committed ncu capture (which
+        # carries its own step count) × the Newton steps this run's launch executed
+        tr = measured_traffic(args.workload)
+        traffic = float(tr["dram_bytes_per_newton_step"]) * tm["newton_steps"] if tr else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -339,6 +559,8 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "mcp_solve_kernel", "achieved": achieved_tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
                          "traffic": traffic,
+                         "traffic_source": (tr or {}).get("source"),
+                         "algorithmic_io_bytes": io_bytes,
                          "peak_source": "measured now on this device by libmcpb200's DFMA probe (MEASURED_PEAKS.json "
                                         "has no FP64 entry)",
                          "kernel_ms": kernel_ms_last,
@@ -347,9 +569,16 @@ def main():
                                     "unit": "GB/s", "frac": io_bytes / (tm["kernel_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                     "peak_source": peak_src}},
         }
+        if world == 1 and not args.no_other_workloads and args.workload == "lane_change":
+            try:
+                line["config"]["other_workloads"] = other_workloads(local, fp64_peak, peaks["hbm_gbs"])
+            except Exception as ex:     # the headline must survive a failure in the extras — but say so
+                line["config"]["other_workloads"] = {"error": f"{type(ex).__name__}: {ex}"}
         if not args.no_cpu_baseline:
             cb, _ = cpu_baseline(mcp, Θ_host, min(args.cpu_sample, B))
             line["cpu_baseline"] = cb
+            c1, _ = cpu_baseline(mcp, Θ_host, min(max(args.cpu_sample // 8, 64), B), threads=1)
+            line["cpu_baseline_1core"] = c1
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -173,6 +174,36 @@ struct DeviceGuard {
   }
   ~DeviceGuard() {
     }
+};
+
+// Page-locks caller-owned PAGEABLE host arrays for the duration of one call (cudaHostRegister) so that the
+// cudaMemcpyAsync of a Julia / numpy caller's arrays runs at full PCIe speed and truly asynchronously, as it does for
+// the pinned buffers of bench.py.  Already pinned / registered / managed / device memory is left alone.  A failed
+// registration is not an error: the copy then takes CUDA's pageable path.  MCPB200_HOST_REGISTER=0 disables it.
+struct HostPin {
+  std::vector<void*> regs;
+  static bool enabled() {
+    static const bool on = [] {
+      const char* e = getenv("MCPB200_HOST_REGISTER");
+      return !(e && atoi(e) == 0);
+    }();
+    return on;
+  }
+  void pin(const void* p, size_t bytes) {
+    if (!p || bytes < (1u << 20) || !enabled()) return;   // small arrays: the registration costs more than it saves
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (attr.type != cudaMemoryTypeUnregistered) return;
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) regs.push_back(const_cast<void*>(p));
+    else cudaGetLastError();
+  }
+  ~HostPin() {
+    for (void* p : regs)
+      if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+  }
 };
 
 int set_err(mcpb200_problem* h, int code, const std::string& msg) {
@@ -805,6 +836,32 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
   std::vector<std::string> errs(shards.size());
   std::vector<float> h2d(shards.size(), 0), d2h(shards.size(), 0);
   std::mutex state_mu;
+  // Pageable caller arrays: the inputs are page-locked before the uploads, the (much larger) outputs while the solve
+  // kernels run — the shard workers wait for `outputs_pinned` before they queue their downloads.
+  HostPin pins;
+  {
+    DeviceGuard g0;
+    if (!shards.empty()) cudaSetDevice(shards[0].dev);
+    pins.pin(theta, (size_t)B * nt * 8);
+    pins.pin(x0, (size_t)B * nx * 8);
+    pins.pin(y0, (size_t)B * ny * 8);
+    pins.pin(s0, (size_t)B * ny * 8);
+  }
+  std::mutex pin_mu;
+  std::condition_variable pin_cv;
+  bool outputs_pinned = false;
+  auto pin_outputs = [&] {
+    pins.pin(x_out, (size_t)B * nx * 8);
+    pins.pin(y_out, (size_t)B * ny * 8);
+    pins.pin(s_out, (size_t)B * ny * 8);
+    pins.pin(kkt_out, (size_t)B * 8);
+    pins.pin(eps_out, (size_t)B * 8);
+    {
+      std::lock_guard<std::mutex> l(pin_mu);
+      outputs_pinned = true;
+    }
+    pin_cv.notify_all();
+  };
   auto work = [&](size_t i) {
     const Shard sh = shards[i];
     DeviceState* st = nullptr;
@@ -857,6 +914,12 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
       if (rcs[i]) errs[i] = h->err;
     }
     if (rcs[i]) return;
+    if (shards.size() == 1) {
+      pin_outputs();   // single device: this thread pins the outputs itself, in the shadow of the kernel it just launched
+    } else {
+      std::unique_lock<std::mutex> l(pin_mu);
+      pin_cv.wait(l, [&] { return outputs_pinned; });
+    }
     if ((e = cudaMemcpyAsync(x_out + sh.begin * nx, st->x.p, n * nx * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H x", e);
     if (ny && (e = cudaMemcpyAsync(y_out + sh.begin * ny, st->y.p, n * ny * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H y", e);
     if (ny && (e = cudaMemcpyAsync(s_out + sh.begin * ny, st->s.p, n * ny * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H s", e);
@@ -876,6 +939,8 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
   } else {
     std::vector<std::thread> ts;
     for (size_t i = 0; i < shards.size(); ++i) ts.emplace_back(work, i);
+    cudaSetDevice(shards[0].dev);
+    pin_outputs();   // (the workers that failed early never wait; the others are released here)
     for (auto& t : ts) t.join();
   }
   for (size_t i = 0; i < shards.size(); ++i) {

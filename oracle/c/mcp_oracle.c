@@ -38,6 +38,9 @@ typedef struct {
   int32_t jz_nnz;
   const int32_t *jz_rows, *jz_cols, *jz_nodes;
   const int32_t* colperm; /* [n] fill-reducing column order, or NULL for natural */
+  /* optional: F!/∇F_z! as COMPILED straight-line C generated from the tape (oracle/c_emit.py) — the analogue of the
+   * reference's build_function output (src/mcp.jl:82-120); NULL ⇒ the tape is interpreted */
+  void (*eval_fn)(const double* x, const double* y, const double* th, double* gh, double* jz);
 } oracle_problem;
 
 typedef struct {
@@ -323,7 +326,7 @@ static double ftb_linesearch(const double* v, const double* d, int n, double tol
 
 typedef struct {
   splu_t lu;
-  double *vals, *Ax, *F, *dz, *work, *x, *y, *s;
+  double *vals, *Ax, *F, *dz, *work, *x, *y, *s, *gh, *jz;
 } thread_ws;
 
 static void ws_init(thread_ws* W, const setup_t* S) {
@@ -337,11 +340,14 @@ static void ws_init(thread_ws* W, const setup_t* S) {
   W->x = malloc(sizeof(double) * (P->nx + 1));
   W->y = malloc(sizeof(double) * (P->ny + 1));
   W->s = malloc(sizeof(double) * (P->ny + 1));
+  W->gh = malloc(sizeof(double) * (P->nx + P->ny + 1));
+  W->jz = malloc(sizeof(double) * (P->jz_nnz + 1));
 }
 
 static void ws_free(thread_ws* W) {
   splu_free(&W->lu);
   free(W->vals); free(W->Ax); free(W->F); free(W->dz); free(W->work); free(W->x); free(W->y); free(W->s);
+  free(W->gh); free(W->jz);
 }
 
 /* `solve(::InteriorPoint, mcp, θ; …)` — src/solver.jl:35-122 */
@@ -360,16 +366,22 @@ static void solve_one(const setup_t* S, thread_ws* W, const oracle_opts* o, cons
     int inner = 1; /* :72 */
     status = 0;    /* :73 */
     while (kkt > eps && inner < o->max_inner_iters) { /* :75 */
-      eval_tape(S, x, y, th, W->vals);
+      if (P->eval_fn) {
+        P->eval_fn(x, y, th, W->gh, W->jz);
+      } else {
+        eval_tape(S, x, y, th, W->vals);
+        for (int i = 0; i < nx + ny; ++i) W->gh[i] = W->vals[P->gh_nodes[i]];
+        for (int k = 0; k < P->jz_nnz; ++k) W->jz[k] = W->vals[P->jz_nodes[k]];
+      }
       /* F = [G; H − s; s∘y − ϵ]   (:79, src/mcp.jl:76-80) */
-      for (int i = 0; i < nx; ++i) F[i] = W->vals[P->gh_nodes[i]];
+      for (int i = 0; i < nx; ++i) F[i] = W->gh[i];
       for (int k = 0; k < ny; ++k) {
-        F[nx + k] = W->vals[P->gh_nodes[nx + k]] - s[k];
+        F[nx + k] = W->gh[nx + k] - s[k];
         F[nx + ny + k] = s[k] * y[k] - eps;
       }
       /* A = ∇F + tol·I   (:80-81) */
       memset(W->Ax, 0, sizeof(double) * S->nnzA);
-      for (int k = 0; k < P->jz_nnz; ++k) W->Ax[S->slot_jz[k]] += W->vals[P->jz_nodes[k]];
+      for (int k = 0; k < P->jz_nnz; ++k) W->Ax[S->slot_jz[k]] += W->jz[k];
       for (int k = 0; k < ny; ++k) {
         W->Ax[S->slot_mI[k]] += -1.0;
         W->Ax[S->slot_S[k]] += s[k];

@@ -22,7 +22,7 @@ class _Problem(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nt", C.c_int32), ("n_nodes", C.c_int32),
                 ("op", _i32p), ("a", _i32p), ("b", _i32p), ("consts", _f64p), ("gh_nodes", _i32p),
                 ("jz_nnz", C.c_int32), ("jz_rows", _i32p), ("jz_cols", _i32p), ("jz_nodes", _i32p),
-                ("colperm", _i32p)]
+                ("colperm", _i32p), ("eval_fn", C.c_void_p)]
 
 
 class _Opts(C.Structure):
@@ -30,11 +30,29 @@ class _Opts(C.Structure):
                 ("tightening_rate", C.c_double), ("loosening_rate", C.c_double), ("min_stepsize", C.c_double)]
 
 
+def cpu_tag() -> str:
+    """The host CPU's ISA flags: `-march=native` objects built on another machine (this container vs the GPU box) are rebuilt."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()[:12]
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+    stamp = os.path.join(HERE, "_build", "cpu.txt")
+    same_cpu = os.path.exists(stamp) and open(stamp).read() == cpu_tag()
+    if force or not same_cpu or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        force = force or not same_cpu
         res = subprocess.run(["make", "-C", HERE, "-B" if force else "-s"], capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("building the C oracle failed:\n" + res.stdout + res.stderr)
+        with open(stamp, "w") as f:
+            f.write(cpu_tag())
     return LIB
 
 
@@ -72,7 +90,7 @@ def column_ordering(ir) -> np.ndarray:
 
 
 def solve_batch(ir, Θ, x0=None, y0=None, s0=None, tol=1e-4, max_inner_iters=20, max_outer_iters=50,
-                tightening_rate=0.1, loosening_rate=0.5, min_stepsize=1e-4, nthreads=0, colperm=None):
+                tightening_rate=0.1, loosening_rate=0.5, min_stepsize=1e-4, nthreads=0, colperm=None, compiled=True):
     """Batched `solve(InteriorPoint(), mcp, θ)` over the columns of Θ (nθ×B) on the host cores."""
     lib = _load()
     Θ = np.asfortranarray(np.asarray(Θ, dtype=np.float64).reshape(ir.ntheta, -1))
@@ -101,8 +119,12 @@ def solve_batch(ir, Θ, x0=None, y0=None, s0=None, tol=1e-4, max_inner_iters=20,
                 ir._oracle_colperm = colperm
             except Exception:
                 pass
+    fn = None
+    if compiled:   # F!/∇F_z! as generated, compiled C; falls back to the interpreter for huge tapes
+        from . import c_emit
+        fn = c_emit.compiled_eval(ir, cpu_tag())
     p = _Problem(ir.nx, ir.ny, ir.ntheta, len(ir.op), i32(ir.op), i32(ir.a), i32(ir.b), f64(ir.consts),
-                 i32(ir.gh_nodes), len(ir.jz_rows), i32(ir.jz_rows), i32(ir.jz_cols), i32(ir.jz_nodes), i32(colperm))
+                 i32(ir.gh_nodes), len(ir.jz_rows), i32(ir.jz_rows), i32(ir.jz_cols), i32(ir.jz_nodes), i32(colperm), fn)
     o = _Opts(tol, max_inner_iters, max_outer_iters, tightening_rate, loosening_rate, min_stepsize)
     nx, ny = ir.nx, ir.ny
     x = np.empty((nx, B), order="F")
