@@ -129,14 +129,14 @@ def cpu_baseline(mcp, Θ, sample: int, threads: int = 0):
     CO.build()
     threads = threads or host_threads()
     Θs = np.asfortranarray(Θ[:, :sample])
-    CO.solve_batch(mcp.ir, Θs[:, :8], tol=TOL, nthreads=threads)      # warm-up (column ordering, page-in)
+    CO.solve_batch(mcp.ir, Θs[:, :8], tol=TOL, nthreads=threads, compiled=True)      # warm-up (column ordering, gcc, page-in)
     t0 = time.perf_counter()
-    r = CO.solve_batch(mcp.ir, Θs, tol=TOL, nthreads=threads)
+    r = CO.solve_batch(mcp.ir, Θs, tol=TOL, nthreads=threads, compiled=True)
     dt = time.perf_counter() - t0
     solved = int((r.status == 0).sum())
     return {"value": solved / dt, "unit": UNIT, "cores": int(r.threads), "kind": "port",
             "sample": f"first {Θs.shape[1]} θ of the bench batch, {solved} converged, {dt:.2f} s wall, "
-                      f"C restatement of src/solver.jl (Julia cannot run in this image), OpenMP over θ"}, r
+                      f"C restatement of src/solver.jl with F/∇F as generated C, -O3 -march=native (Julia cannot run in this image), OpenMP over θ"}, r
 
 
 def run_reference(args):
@@ -151,11 +151,11 @@ def run_reference(args):
     CO.build()
     threads = host_threads()
     for _ in range(args.warmup):
-        CO.solve_batch(mcp.ir, Θ[:, :min(sample, 64)], tol=TOL, nthreads=threads)
+        CO.solve_batch(mcp.ir, Θ[:, :min(sample, 64)], tol=TOL, nthreads=threads, compiled=True)
     t0 = time.perf_counter()
     solved = 0
     for _ in range(args.steps):
-        r = CO.solve_batch(mcp.ir, Θ, tol=TOL, nthreads=threads)
+        r = CO.solve_batch(mcp.ir, Θ, tol=TOL, nthreads=threads, compiled=True)
         solved += int((r.status == 0).sum())
     dt = time.perf_counter() - t0
     v = solved / dt

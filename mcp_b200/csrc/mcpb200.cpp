@@ -14,7 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
-#include <condition_variable>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -182,7 +182,7 @@ struct DeviceGuard {
 // registration is not an error: the copy then takes CUDA's pageable path.  MCPB200_HOST_REGISTER=0 disables it.
 struct HostPin {
   std::vector<void*> regs;
-  static bool enabled() {
+  static bool enabled() {   // MCPB200_HOST_REGISTER=0: never page-lock caller memory
     static const bool on = [] {
       const char* e = getenv("MCPB200_HOST_REGISTER");
       return !(e && atoi(e) == 0);
@@ -203,6 +203,58 @@ struct HostPin {
   ~HostPin() {
     for (void* p : regs)
       if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+  }
+};
+
+bool is_pageable_host(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// Device → host download of one shard's slice of a caller array, in two stages so that every page-locking call of a
+// shard is made BEFORE its first copy is queued (a cudaHostRegister issued behind a queued copy waits for the stream).
+// A PAGEABLE destination (a Julia or numpy caller's plain array) is page-locked — only the page-aligned INTERIOR of the
+// slice, so that the registrations of neighbouring shards (one host thread per device, running concurrently, in the
+// shadow of their kernels) never share a page — and copied in three parts: the interior asynchronously at full PCIe
+// speed, the two ragged edges (< one page each) through CUDA's pageable path.  The registrations last for the call
+// (unregistering costs ≈ 0.15 ms per MB: ≈ 200 ms for the bench batch's 1.4 GB — keeping them between calls would save
+// that but is unsafe without owning the arrays' lifetime, so it is not done).
+struct Download {
+  char* dst = nullptr;
+  const char* src = nullptr;
+  size_t bytes = 0;
+  uintptr_t i0 = 0, i1 = 0;   // registered interior [i0, i1), or empty
+  void prepare(HostPin& pins, void* dst_, const void* src_, size_t bytes_) {
+    constexpr size_t PAGE = 4096;
+    dst = (char*)dst_;
+    src = (const char*)src_;
+    bytes = bytes_;
+    i0 = i1 = 0;
+    if (bytes < (4u << 20) || !HostPin::enabled() || !is_pageable_host(dst)) return;
+    const uintptr_t a0 = (uintptr_t)dst, a1 = a0 + bytes;
+    const uintptr_t b0 = (a0 + PAGE - 1) / PAGE * PAGE, b1 = a1 / PAGE * PAGE;
+    if (b1 <= b0) return;
+    if (cudaHostRegister((void*)b0, b1 - b0, cudaHostRegisterPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    pins.regs.push_back((void*)b0);   // released when the shard's worker returns (after its stream sync)
+    i0 = b0;
+    i1 = b1;
+  }
+  cudaError_t issue(cudaStream_t sm) const {
+    if (!bytes) return cudaSuccess;
+    if (i1 <= i0) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sm);
+    const uintptr_t a0 = (uintptr_t)dst, a1 = a0 + bytes;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync((void*)i0, src + (i0 - a0), i1 - i0, cudaMemcpyDeviceToHost, sm)) != cudaSuccess) return e;
+    if (i0 > a0 && (e = cudaMemcpyAsync(dst, src, i0 - a0, cudaMemcpyDeviceToHost, sm)) != cudaSuccess) return e;
+    if (a1 > i1 && (e = cudaMemcpyAsync((void*)i1, src + (i1 - a0), a1 - i1, cudaMemcpyDeviceToHost, sm)) != cudaSuccess) return e;
+    return cudaSuccess;
   }
 };
 
@@ -836,8 +888,8 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
   std::vector<std::string> errs(shards.size());
   std::vector<float> h2d(shards.size(), 0), d2h(shards.size(), 0);
   std::mutex state_mu;
-  // Pageable caller arrays: the inputs are page-locked before the uploads, the (much larger) outputs while the solve
-  // kernels run — the shard workers wait for `outputs_pinned` before they queue their downloads.
+  // Pageable caller arrays: the (small) inputs are page-locked for the duration of the call; the (much larger) outputs
+  // are page-locked per shard by the shard's own host thread while its kernels run (download()).
   HostPin pins;
   {
     DeviceGuard g0;
@@ -847,21 +899,6 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
     pins.pin(y0, (size_t)B * ny * 8);
     pins.pin(s0, (size_t)B * ny * 8);
   }
-  std::mutex pin_mu;
-  std::condition_variable pin_cv;
-  bool outputs_pinned = false;
-  auto pin_outputs = [&] {
-    pins.pin(x_out, (size_t)B * nx * 8);
-    pins.pin(y_out, (size_t)B * ny * 8);
-    pins.pin(s_out, (size_t)B * ny * 8);
-    pins.pin(kkt_out, (size_t)B * 8);
-    pins.pin(eps_out, (size_t)B * 8);
-    {
-      std::lock_guard<std::mutex> l(pin_mu);
-      outputs_pinned = true;
-    }
-    pin_cv.notify_all();
-  };
   auto work = [&](size_t i) {
     const Shard sh = shards[i];
     DeviceState* st = nullptr;
@@ -872,6 +909,7 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
     }
     if (rcs[i]) return;
     auto fail = [&](const char* what, cudaError_t e) {
+      if (st && st->stream) cudaStreamSynchronize(st->stream);   // nothing may still be copying into memory about to be unregistered
       rcs[i] = MCPB200_ERR_CUDA;
       errs[i] = std::string(what) + ": " + cudaGetErrorString(e);
       cudaGetLastError();
@@ -914,22 +952,27 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
       if (rcs[i]) errs[i] = h->err;
     }
     if (rcs[i]) return;
-    if (shards.size() == 1) {
-      pin_outputs();   // single device: this thread pins the outputs itself, in the shadow of the kernel it just launched
-    } else {
-      std::unique_lock<std::mutex> l(pin_mu);
-      pin_cv.wait(l, [&] { return outputs_pinned; });
-    }
-    if ((e = cudaMemcpyAsync(x_out + sh.begin * nx, st->x.p, n * nx * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H x", e);
-    if (ny && (e = cudaMemcpyAsync(y_out + sh.begin * ny, st->y.p, n * ny * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H y", e);
-    if (ny && (e = cudaMemcpyAsync(s_out + sh.begin * ny, st->s.p, n * ny * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H s", e);
+    HostPin out_pins;
+    const bool dbg = getenv("MCPB200_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    Download dx, dy, ds;
+    dx.prepare(out_pins, x_out + sh.begin * nx, st->x.p, n * nx * 8);
+    if (ny) dy.prepare(out_pins, y_out + sh.begin * ny, st->y.p, n * ny * 8);
+    if (ny) ds.prepare(out_pins, s_out + sh.begin * ny, st->s.p, n * ny * 8);
+    const double t1 = now();
+    if ((e = dx.issue(sm))) return fail("D2H x", e);
+    if ((e = dy.issue(sm))) return fail("D2H y", e);
+    if ((e = ds.issue(sm))) return fail("D2H s", e);
     if ((e = cudaMemcpyAsync(kkt_out + sh.begin, st->kkt.p, n * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H kkt", e);
     if ((e = cudaMemcpyAsync(eps_out + sh.begin, st->eps.p, n * 8, cudaMemcpyDeviceToHost, sm))) return fail("D2H eps", e);
     if ((e = cudaMemcpyAsync(outer_out + sh.begin, st->outer.p, n * 4, cudaMemcpyDeviceToHost, sm))) return fail("D2H outer", e);
     if ((e = cudaMemcpyAsync(status_out + sh.begin, st->status.p, n * 4, cudaMemcpyDeviceToHost, sm))) return fail("D2H status", e);
     if (steps_out && (e = cudaMemcpyAsync(steps_out + sh.begin, st->steps.p, n * 4, cudaMemcpyDeviceToHost, sm))) return fail("D2H steps", e);
     cudaEventRecord(st->ev_d2h1, sm);
+    const double t2 = now();
     if ((e = cudaStreamSynchronize(sm))) return fail("solve kernel / stream sync", e);
+    if (dbg) fprintf(stderr, "[mcpb200] dev %d: register %.1f ms, issue %.1f ms, sync %.1f ms\n", sh.dev, t1 - t0, t2 - t1, now() - t2);
     cudaEventElapsedTime(&h2d[i], st->ev_h2d0, st->ev_h2d1);
     cudaEventElapsedTime(&d2h[i], st->ev1, st->ev_d2h1);
   };
@@ -939,8 +982,6 @@ int mcpb200_solve_batched(mcpb200_handle h, int64_t B, const double* theta, cons
   } else {
     std::vector<std::thread> ts;
     for (size_t i = 0; i < shards.size(); ++i) ts.emplace_back(work, i);
-    cudaSetDevice(shards[0].dev);
-    pin_outputs();   // (the workers that failed early never wait; the others are released here)
     for (auto& t : ts) t.join();
   }
   for (size_t i = 0; i < shards.size(); ++i) {

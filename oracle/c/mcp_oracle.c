@@ -40,7 +40,7 @@ typedef struct {
   const int32_t* colperm; /* [n] fill-reducing column order, or NULL for natural */
   /* optional: F!/∇F_z! as COMPILED straight-line C generated from the tape (oracle/c_emit.py) — the analogue of the
    * reference's build_function output (src/mcp.jl:82-120); NULL ⇒ the tape is interpreted */
-  void (*eval_fn)(const double* x, const double* y, const double* th, double* gh, double* jz);
+  void (*eval_fn)(const double* x, const double* y, const double* th, double* gh, double* jz, double* scratch /* n_nodes */);
 } oracle_problem;
 
 typedef struct {
@@ -367,7 +367,7 @@ static void solve_one(const setup_t* S, thread_ws* W, const oracle_opts* o, cons
     status = 0;    /* :73 */
     while (kkt > eps && inner < o->max_inner_iters) { /* :75 */
       if (P->eval_fn) {
-        P->eval_fn(x, y, th, W->gh, W->jz);
+        P->eval_fn(x, y, th, W->gh, W->jz, W->vals);
       } else {
         eval_tape(S, x, y, th, W->vals);
         for (int i = 0; i < nx + ny; ++i) W->gh[i] = W->vals[P->gh_nodes[i]];

@@ -16,7 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
-MAX_NODES = 60000      # beyond this gcc's compile time explodes; the interpreter is used instead
+MAX_NODES = 400000     # beyond this the interpreter is used instead
 
 _BIN = {4: "+", 5: "-", 6: "*", 7: "/"}
 _FUN = {9: "sqrt", 10: "exp", 11: "log", 12: "sin", 13: "cos"}
@@ -43,11 +43,25 @@ def emit_source(ir) -> str:
             stack += [int(ir.a[n]), int(ir.b[n])]
         elif op >= 8:
             stack.append(int(ir.a[n]))
-    out = ["#include <math.h>",
-           "static inline double powi_(double a, int n) { double r = 1.0; int neg = n < 0; if (neg) n = -n; "
-           "while (n) { if (n & 1) r *= a; a *= a; n >>= 1; } return neg ? 1.0 / r : r; }",
-           "void mcp_eval(const double* restrict x, const double* restrict y, const double* restrict th, "
-           "double* restrict gh, double* restrict jz) {"]
+    # Values live in a caller-provided scratch array and the code is split into functions of ≤ CHUNK statements:
+    # gcc's compile time is super-linear in the size of one straight-line function (a 16 k-statement QP evaluator
+    # took 570 s at -O2 as a single function, ≈ 2 s this way).
+    CHUNK = 200
+    head = ["#include <math.h>",
+            "static inline double powi_(double a, int n) { double r = 1.0; int neg = n < 0; if (neg) n = -n; "
+            "while (n) { if (n & 1) r *= a; a *= a; n >>= 1; } return neg ? 1.0 / r : r; }"]
+    body, funcs = [], []
+
+    def flush():
+        if body:
+            name = f"part{len(funcs)}"
+            funcs.append(name)
+            head.append(f"static void {name}(const double* restrict x, const double* restrict y, const double* restrict th, "
+                        "double* restrict v, double* restrict gh, double* restrict jz) {")
+            head.extend(body)
+            head.append("}")
+            body.clear()
+
     for n in np.nonzero(need)[0]:
         op, a, b = int(ir.op[n]), int(ir.a[n]), int(ir.b[n])
         if op == 0:
@@ -59,22 +73,32 @@ def emit_source(ir) -> str:
         elif op == 3:
             e = f"th[{a}]"
         elif op in _BIN:
-            e = f"v{a} {_BIN[op]} v{b}"
+            e = f"v[{a}] {_BIN[op]} v[{b}]"
         elif op == 8:
-            e = f"-v{a}"
+            e = f"-v[{a}]"
         elif op in _FUN:
-            e = f"{_FUN[op]}(v{a})"
+            e = f"{_FUN[op]}(v[{a}])"
         elif op == 14:
-            e = f"powi_(v{a}, {b})"
+            e = f"powi_(v[{a}], {b})"
         else:
             e = "NAN"
-        out.append(f"  const double v{n} = {e};")
+        body.append(f"  v[{n}] = {e};")
+        if len(body) >= CHUNK:
+            flush()
     for i, n in enumerate(ir.gh_nodes):
-        out.append(f"  gh[{i}] = v{int(n)};")
+        body.append(f"  gh[{i}] = v[{int(n)}];")
+        if len(body) >= CHUNK:
+            flush()
     for k, n in enumerate(ir.jz_nodes):
-        out.append(f"  jz[{k}] = v{int(n)};")
-    out.append("}")
-    return "\n".join(out) + "\n"
+        body.append(f"  jz[{k}] = v[{int(n)}];")
+        if len(body) >= CHUNK:
+            flush()
+    flush()
+    head.append(f"int mcp_eval_scratch(void) {{ return {len(ir.op)}; }}")
+    head.append("void mcp_eval(const double* x, const double* y, const double* th, double* gh, double* jz, double* v) {")
+    head.extend(f"  {f}(x, y, th, v, gh, jz);" for f in funcs)
+    head.append("}")
+    return "\n".join(head) + "\n"
 
 
 _cache = {}

@@ -90,7 +90,7 @@ def column_ordering(ir) -> np.ndarray:
 
 
 def solve_batch(ir, Θ, x0=None, y0=None, s0=None, tol=1e-4, max_inner_iters=20, max_outer_iters=50,
-                tightening_rate=0.1, loosening_rate=0.5, min_stepsize=1e-4, nthreads=0, colperm=None, compiled=True):
+                tightening_rate=0.1, loosening_rate=0.5, min_stepsize=1e-4, nthreads=0, colperm=None, compiled=False):
     """Batched `solve(InteriorPoint(), mcp, θ)` over the columns of Θ (nθ×B) on the host cores."""
     lib = _load()
     Θ = np.asfortranarray(np.asarray(Θ, dtype=np.float64).reshape(ir.ntheta, -1))
@@ -120,7 +120,8 @@ def solve_batch(ir, Θ, x0=None, y0=None, s0=None, tol=1e-4, max_inner_iters=20,
             except Exception:
                 pass
     fn = None
-    if compiled:   # F!/∇F_z! as generated, compiled C; falls back to the interpreter for huge tapes
+    if compiled:   # F!/∇F_z! as generated, compiled C — the timing legs of bench.py ask for it; the tests keep
+        # the interpreted tape (bit-identical results, no gcc run: the big QP evaluators take a minute to compile)
         from . import c_emit
         fn = c_emit.compiled_eval(ir, cpu_tag())
     p = _Problem(ir.nx, ir.ny, ir.ntheta, len(ir.op), i32(ir.op), i32(ir.a), i32(ir.b), f64(ir.consts),

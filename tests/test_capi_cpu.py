@@ -237,7 +237,7 @@ def test_adjoint_tables_are_a_column_major_view_of_the_dests(monkeypatch, tmp_pa
     assert m["HAS_ADJOINT"] == "1" and m["KL"] == m["KU"]
 
     def table(name):
-        body = re.search(r"__device__ const int %s\[\d+\] = \{([^}]*)\}" % name, src).group(1)
+        body = re.search(r"__device__ const (?:int|short) %s\[\d+\] = \{([^}]*)\}" % name, src).group(1)
         return np.array([int(v) for v in body.replace("\n", "").split(",")])
 
     nd, n, wc = int(m["ND"]), int(m["NRED"]), int(m["WC"])
