@@ -2240,19 +2240,31 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
       const double f2 = hh[k] - s[k];             // H − s        (src/mcp.jl:78)
       const double f3 = s[k] * y[k] - eps;        // s∘y − ϵ      (src/mcp.jl:79)
       const double yt = y[k] + tol;               // (3,3) block diag(y) + tol·I  (:81)
+#if FULL_Y
+      // mode B (∇_y H ≠ 0): only δs is eliminated.  The per-constraint array holds s/(y+tol), which the assembly adds
+      // (with tol) to the diagonal of the H rows; w is the right-hand side of row nx+k
+      dinv[k] = s[k] / yt;
+      w[k] = -f2 - f3 / yt;
+#else
       const double di = 1.0 / (tol + s[k] / yt);  // D⁻¹, D = (2,2) block tol·I + S (Y+tol)⁻¹
       dinv[k] = di;
       w[k] = di * (-f2 - f3 / yt);
+#endif
       fmax_ = nanmax(fmax_, nanmax(fabs(f2), fabs(f3)));
     }
     const double kkt_new = sub_nanmax(fmax_, smask);  // ‖F‖∞ of the pre-step residual (:107)
     __syncwarp(smask);
     // (∇F + tol·I) δz = −F, condensed to NRED unknowns (:81-83)
     for (int i = sl; i < NRED; i += SUB) {
+#if FULL_Y
+      const int old = R_GROW[i];
+      sol[i] = (old < NX) ? -g[old] : w[old - NX];
+#else
       double r = -g[R_GROW[i]];
 #pragma unroll 4
       for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF_AT(e) * opval(R_CODE[e], jv, th) * w[R_K[e]];
       sol[i] = r;
+#endif
     }
     __syncwarp(smask);  // G (aliased onto the window) is dead from here on: the window becomes scratch
 #if NWIDE > 1
@@ -2277,10 +2289,14 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     if (!failed) {
       // δy = w − D⁻¹ H_x δx ;  δs = −(F₃ + s δy)/(y + tol)
       for (int k = sl; k < NY; k += SUB) {
+#if FULL_Y
+        const double dy = sol[IPERM[NX + k]];
+#else
         double hx = 0.0;
 #pragma unroll 4
         for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * sol[H_COL[e]];
         const double dy = w[k] - dinv[k] * hx;
+#endif
         const double f3 = s[k] * y[k] - eps;
         w[k] = dy;
         dinv[k] = -(f3 + s[k] * dy) / (y[k] + tol);
@@ -2302,7 +2318,12 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 #ifdef EXP_FIXED_STEPS
       if (a_s != 0.0)
 #endif
+#if FULL_Y
+      for (int c = sl; c < NRED; c += SUB)
+        if (PERM[c] < NX) x[PERM[c]] += a_s * sol[c];
+#else
       for (int c = sl; c < NRED; c += SUB) x[PERM[c]] += a_s * sol[c];  // :103 (x uses α_s)
+#endif
 #ifdef EXP_FIXED_STEPS
       if (a_s != 0.0)
 #endif

@@ -872,18 +872,23 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
 
   // ---- blocks of the Jacobian -----------------------------------------------------------------------
-  std::vector<Entry> Gx, Gy, Hx;
+  std::vector<Entry> Gx, Gy, Hx, Hy;
   for (size_t k = 0; k < P.jz_nodes.size(); ++k) {
     const int r = P.jz_rows[k], c = P.jz_cols[k];
     if (r < nx && c < nx) Gx.push_back({r, c, (int)k});
     else if (r < nx) Gy.push_back({r, c - nx, (int)k});
     else if (c < nx) Hx.push_back({r - nx, c, (int)k});
-    else
-      return fail(MCPB200_ERR_UNSUPPORTED,
-                  "H depends on y (∇_y H ≠ 0): only the condensed mode (∇_y H ≡ 0, true for every reference "
-                  "config) is implemented in this round");
+    else Hy.push_back({r - nx, c - nx, (int)k});
   }
-  const int N = nx;
+  // ∇_y H ≢ 0 (the reference accepts any H(x, y; θ), src/mcp.jl:27-52,76-80 — none of its own configs has it): mode B,
+  // the (nx+ny)-dimensional system with only δs eliminated.  MCPB200_FULL_Y=1 forces it (tests).
+  P.full_y = !Hy.empty();
+  if (const char* e = getenv("MCPB200_FULL_Y")) P.full_y = P.full_y || atoi(e) != 0;
+  if (P.full_y && P.has_jt) {   // the sensitivity kernels implement the condensed mode only
+    P.has_jt = false;
+    P.sens_blocked = true;
+  }
+  const int N = P.full_y ? nx + ny : nx;
   P.N = N;
 
   // ---- structure of C = G_x + tol·I − G_y D⁻¹ H_x ------------------------------------------------------
@@ -900,13 +905,24 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     const Operand& o = P.jz_opnd[e.idx];
     dest[{e.row, e.col}].push_back({o.coef, o.code, -1, -1});
   }
-  for (int k = 0; k < ny; ++k)
-    for (auto& g : gy_by_k[k])
-      for (auto& h : hx_by_k[k]) {
-        const Operand& og = P.jz_opnd[g.idx];
-        const Operand& oh = P.jz_opnd[h.idx];
-        dest[{g.row, h.col}].push_back({-og.coef * oh.coef, og.code, oh.code, k});
-      }
+  if (P.full_y) {
+    auto put = [&](int r, int c, int idx) {
+      const Operand& o = P.jz_opnd[idx];
+      dest[{r, c}].push_back({o.coef, o.code, -1, -1});
+    };
+    for (auto& e : Gy) put(e.row, nx + e.col, e.idx);
+    for (auto& e : Hx) put(nx + e.row, e.col, e.idx);
+    for (auto& e : Hy) put(nx + e.row, nx + e.col, e.idx);
+    for (int k = 0; k < ny; ++k) dest[{nx + k, nx + k}].push_back({1.0, -1, -1, k});   // + s_k/(y_k+tol): 1·[dinv_k·1]
+  } else {
+    for (int k = 0; k < ny; ++k)
+      for (auto& g : gy_by_k[k])
+        for (auto& h : hx_by_k[k]) {
+          const Operand& og = P.jz_opnd[g.idx];
+          const Operand& oh = P.jz_opnd[h.idx];
+          dest[{g.row, h.col}].push_back({-og.coef * oh.coef, og.code, oh.code, k});
+        }
+  }
   std::vector<std::pair<int, int>> pattern;
   pattern.reserve(dest.size());
   for (auto& kv : dest) pattern.push_back(kv.first);
@@ -950,8 +966,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     size_t n_schur = 0;
     for (auto& kv : dest)
       for (auto& t : kv.second) n_schur += (t.k >= 0);
-    P.dense_schur = (P.R == N && P.WC == N && n_schur > 4 * dest.size()) ? 1 : 0;
-    if (const char* e = getenv("MCPB200_DENSE_SCHUR")) P.dense_schur = (atoi(e) != 0) && P.R == N && P.WC == N;
+    P.dense_schur = (!P.full_y && P.R == N && P.WC == N && n_schur > 4 * dest.size()) ? 1 : 0;
+    if (const char* e = getenv("MCPB200_DENSE_SCHUR")) P.dense_schur = (atoi(e) != 0) && P.R == N && P.WC == N && !P.full_y;
     P.dense_kernel = (P.dense_schur && N <= 112 && ny <= 128) ? 1 : 0;   // thread mappings of the dense kernel
     if (const char* e = getenv("MCPB200_DENSE_KERNEL")) P.dense_kernel = (atoi(e) != 0) && P.dense_schur && N <= 112 && ny <= 128;
     if (P.dense_schur)
@@ -962,7 +978,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
   // Problems of a few unknowns (the README QP: nx = ny = 2): one THREAD per instance, everything in registers, all
   // tables turned into straight-line code (kernel_template.cuh, TINY_KERNEL).  MCPB200_TINY=0 disables it.
-  P.tiny_kernel = (!P.dense_kernel && !P.dense_schur && N <= 6 && ny <= 8 && nt <= 32 && P.op.size() <= 4000) ? 1 : 0;
+  P.tiny_kernel = (!P.full_y && !P.dense_kernel && !P.dense_schur && N <= 6 && ny <= 8 && nt <= 32 && P.op.size() <= 4000) ? 1 : 0;
   if (const char* e = getenv("MCPB200_TINY")) P.tiny_kernel = P.tiny_kernel && atoi(e) != 0;
   P.nrhs_sens = P.has_jt ? std::max(1, std::min(nt, kMaxSensRhs)) : 1;
   if (P.has_jt) {
@@ -1014,6 +1030,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     for (int i = 0; i < N; ++i) {
       const int old = P.perm[i];
       P.r_grow.push_back(old);
+      if (!P.full_y)
       for (auto& e : gy_by_row[old]) {
         P.r_coef.push_back(P.jz_opnd[e.idx].coef);
         P.r_code.push_back(P.jz_opnd[e.idx].code);
@@ -1023,6 +1040,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     }
     P.h_ptr.push_back(0);
     for (int k = 0; k < ny; ++k) {
+      if (!P.full_y)
       for (auto& e : hx_by_k[k]) {
         P.h_coef.push_back(P.jz_opnd[e.idx].coef);
         P.h_code.push_back(P.jz_opnd[e.idx].code);
@@ -1427,6 +1445,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
+  os << "#define FULL_Y " << P.full_y << "\n";
   os << "#define TINY_KERNEL " << P.tiny_kernel << "\n";
   os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n#define REGWIN_PW_MAX " << regwin_pw_max << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";

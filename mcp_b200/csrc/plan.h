@@ -45,6 +45,11 @@ struct Plan {
   // ---- condensed system -------------------------------------------------------------------------
   // Mode A (every config of the reference: ∇_y H ≡ 0): eliminate δs and δy, factorise the nx×nx matrix
   //   C = G_x + tol·I − G_y D⁻¹ H_x ,  D = tol + s/(y+tol)        
+  // Mode B (∇_y H ≠ 0, e.g. LCP-style H(x, y)): only δs is eliminated; the (nx+ny)-dimensional system
+  //   [G_x + tol·I, G_y; H_x, H_y + tol·I + diag(s/(y+tol))] [δx; δy] = [−F1; −F2 − F3/(y+tol)]
+  // is factorised by the same banded machinery (the kernel's per-constraint array then holds s/(y+tol) instead of D⁻¹).
+  int full_y = 0;
+  bool sens_blocked = false;          // mode B: the sensitivity kernels are not generated (ERR_UNSUPPORTED)
   int N = 0;                          // reduced dimension
   std::vector<int32_t> perm, iperm;   // perm[new] = old, iperm[old] = new  (fill-reducing ordering)
   int kl = 0, ku = 0;                 // bandwidths in the new ordering

@@ -84,12 +84,19 @@ def test_invalid_ir_is_rejected():
     assert e.value.code == capi.ERR_INVALID_ARGUMENT
 
 
-def test_h_depending_on_y_is_unsupported():
+def test_h_depending_on_y_compiles_in_full_y_mode():
+    """∇_y H ≠ 0 (the reference accepts any H(x, y; θ), `src/mcp.jl:27-52,76-80`): the plan switches to the
+    (nx+ny)-dimensional system with only δs eliminated; sensitivities are not generated in that mode."""
     mcp = PrimalDualMCP(lambda x, y, θ: x - θ - y, lambda x, y, θ: x + 0.5 * y, unconstrained_dimension=1,
                         constrained_dimension=1, parameter_dimension=1)
-    with pytest.raises(capi.MCPB200Error) as e:
-        capi.Handle(mcp.ir, capi.COMPILE_ONLY)
-    assert e.value.code == capi.ERR_UNSUPPORTED
+    h = capi.Handle(mcp.ir, capi.COMPILE_ONLY)
+    src, info = h.source(), h.info()
+    assert _macros(src)["FULL_Y"] == "1" and info["n_reduced"] == 2 and info["has_sensitivities"] == 0
+    h.close()
+    # a problem of the reference's own structure stays in the condensed mode
+    h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["FULL_Y"] == "0" and h.info()["n_reduced"] == 2
+    h.close()
 
 
 def test_no_cpu_fallback():

@@ -615,3 +615,53 @@ def test_gpu_solutions_satisfy_independent_kkt(lane_game):
         assert np.max(np.abs(Hms)) <= 1e-5 and np.max(sy) <= 1e-4 and float(sol.y[:, b] @ H) <= 250 * 1e-4
         checked += 1
     assert checked >= 28
+
+
+def _lcp_like_mcp(compute_sensitivities=False):
+    """A small MCP whose H depends on y (an LCP-style coupling B y): G = M x − θ − Aᵀ y, H = A x − b + B y."""
+    from mcp_b200.mcp import PrimalDualMCP
+    M = np.array([[2.0, 1, 0], [1, 2, 0.5], [0, 0.5, 3]])
+    A = np.array([[1.0, 0, 1], [0, 1, 0], [1, 1, 0]])
+    Bm = np.array([[0.5, 0.1, 0], [0.1, 0.4, 0], [0, 0, 0.3]])
+    b = np.array([1.0, 1, 0.5])
+    return PrimalDualMCP(lambda x, y, θ: M @ x - θ - A.T @ y, lambda x, y, θ: A @ x - b + Bm @ y,
+                         unconstrained_dimension=3, constrained_dimension=3, parameter_dimension=3,
+                         compute_sensitivities=compute_sensitivities)
+
+
+def test_h_depending_on_y_matches_oracle():
+    """∇_y H ≠ 0 (`src/mcp.jl:76-80` allows any H(x, y; θ)): the (nx+ny)-dimensional mode against the Python oracle, which
+    solves the full n×n system as the reference does — same status, identical step counts, x/y/s within 1e-6."""
+    mcp = _lcp_like_mcp()
+    Θ = np.asfortranarray(np.random.default_rng(4).uniform(-1.0, 2.0, (3, 256)))
+    for tol in (1e-4, 1e-6):
+        sol = solve(InteriorPoint(), mcp, Θ, tol=tol)
+        compare_batch(mcp, Θ, sol, tol=tol, min_match=1.0)
+    # sensitivities are refused loudly in this mode, never computed wrongly
+    from mcp_b200 import solve_pullback
+    from mcp_b200.capi import MCPB200Error
+    m2 = _lcp_like_mcp(compute_sensitivities=True)
+    s2 = solve(InteriorPoint(), m2, Θ[:, :4])
+    with pytest.raises(MCPB200Error):
+        solve_pullback(m2, s2, Θ[:, :4], 2 * s2.x, None, None)
+
+
+def test_full_y_mode_on_lane_change_matches_condensed(lane_game, monkeypatch):
+    """The same mode forced (MCPB200_FULL_Y=1) on the lane-change game, a 450-dimensional banded system: it must follow the
+    condensed kernel's trajectory (identical Newton-step counts, x/y/s within 1e-6)."""
+    from mcp_b200 import capi
+    from mcp_b200.solver import _handle
+    mcp = lane_game.mcp
+    Θ = problems.lane_change_thetas(64, seed=12)
+    ref = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    monkeypatch.setenv("MCPB200_FULL_Y", "1")
+    game2 = problems.lane_change_game(compute_sensitivities=False)
+    h = _handle(game2.mcp)
+    assert h.info()["n_reduced"] == 450
+    got = solve(InteriorPoint(), game2.mcp, Θ, tol=1e-6)
+    np.testing.assert_array_equal(got.status, ref.status)
+    ok = ref.status == 0
+    assert np.all(np.abs(got.newton_steps[ok] - ref.newton_steps[ok]) <= 1)
+    for b in np.nonzero(ok)[0]:
+        assert rel_err(got.x[:, b], ref.x[:, b]) <= RTOL and rel_err(got.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(got.s[:, b], ref.s[:, b]) <= RTOL
