@@ -27,7 +27,7 @@
 // State vectors are re-written during the kernel.  In shared memory `__restrict__` is a pure aliasing hint; once
 // they live in global memory (LARGE_STATE) `const T* __restrict__` would licence the non-coherent read-only path
 // (ld.global.nc) and stale reads, so the qualifier is dropped there.
-#if LARGE_STATE
+#if LARGE_STATE || S_GLOBAL
 #define RS
 #else
 #define RS __restrict__
@@ -2020,7 +2020,10 @@ extern "C" __global__ void __launch_bounds__(128) mcp_solve_kernel(const SolvePa
 // of the main loop.  The sub-warps of a warp re-align once per Newton step (the full-warp vote below),
 // so the heavy phases of their two instances execute as the same instructions.
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_solve_kernel(const SolveParams p) {
+#ifndef SOLVE_LB_THREADS
+#define SOLVE_LB_THREADS (SUB * SOLVE_INST * NWIDE)
+#endif
+extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kernel(const SolveParams p) {
   extern __shared__ double smem[];
 #if NWIDE > 1
   // cooperative instances: NWIDE consecutive warps per instance, the first is the leader (runs everything below),
@@ -2046,8 +2049,14 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 #endif
   double* x = S + SOLVE_OFF_X;
   double* y = S + SOLVE_OFF_Y;
+#if S_GLOBAL && !LARGE_STATE
+  // `s` is touched only by lane-strided sweeps: it lives in the instance's global block (coalesced, L1/L2-resident), which
+  // is what lets 20 instead of 16 instances share an SM's shared memory for the lane-change game
+  double* s = p.state + ((size_t)blockIdx.x * SOLVE_INST + slot) * SOLVE_STATE_DOUBLES;
+#else
   double* s = S + SOLVE_OFF_S;
-  double* g = SOLVE_G_IN_WIN ? W : S + SOLVE_OFF_G;  // G rows (alias the window region when they fit)
+#endif
+  // G rows: in `sol` at their permuted positions (SOLVE_G_ON_SOL), else aliasing the window region when they fit
   double* hh = S + SOLVE_OFF_H;       // H rows (alias w: H[k] is consumed where w[k] is produced)
   double* jv = S + SOLVE_OFF_JV;
   double* dinv = S + SOLVE_OFF_DINV;  // D⁻¹, later δs
@@ -2057,6 +2066,7 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
 #else
   double* sol = S + SOLVE_OFF_SOL;    // δx in the permuted ordering
 #endif
+  double* g = SOLVE_G_ON_SOL ? sol : (SOLVE_G_IN_WIN ? W : S + SOLVE_OFF_G);
 #if THETA_IN_SMEM
   double* th = S + SOLVE_OFF_TH;
 #else
@@ -2235,7 +2245,12 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     __syncwarp(smask);
 #endif
     double fmax_ = 0.0;
-    for (int i = sl; i < NX; i += SUB) fmax_ = nanmax(fmax_, fabs(g[i]));
+#if SOLVE_G_ON_SOL && FULL_Y
+    for (int i = sl; i < NRED; i += SUB)
+      if (R_GROW[i] < NX) fmax_ = nanmax(fmax_, fabs(g[i]));   // (the y rows of `sol` hold stale data here)
+#else
+    for (int i = sl; i < NX; i += SUB) fmax_ = nanmax(fmax_, fabs(g[i]));   // (a permutation of the G rows when G lives in sol)
+#endif
     for (int k = sl; k < NY; k += SUB) {
       const double f2 = hh[k] - s[k];             // H − s        (src/mcp.jl:78)
       const double f3 = s[k] * y[k] - eps;        // s∘y − ϵ      (src/mcp.jl:79)
@@ -2258,9 +2273,9 @@ extern "C" __global__ void __launch_bounds__(SUB * SOLVE_INST * NWIDE, 1) mcp_so
     for (int i = sl; i < NRED; i += SUB) {
 #if FULL_Y
       const int old = R_GROW[i];
-      sol[i] = (old < NX) ? -g[old] : w[old - NX];
+      sol[i] = (old < NX) ? -g[SOLVE_G_ON_SOL ? i : old] : w[old - NX];
 #else
-      double r = -g[R_GROW[i]];
+      double r = -g[SOLVE_G_ON_SOL ? i : R_GROW[i]];   // (in place when G lives in sol: row i reads and writes sol[i])
 #pragma unroll 4
       for (int e = R_PTR[i]; e < R_PTR[i + 1]; ++e) r -= R_COEF_AT(e) * opval(R_CODE[e], jv, th) * w[R_K[e]];
       sol[i] = r;

@@ -553,7 +553,7 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   p.scratch = (double*)st->scratch.p;
   p.counters = (unsigned long long*)st->counters.p;
   p.state = nullptr;
-  if (P.large_state) {
+  if (P.large_state || P.state_doubles_solve > 0) {   // (also the S_GLOBAL plans: `s` alone lives in the global block)
     if (st->state.ensure((size_t)st->num_sms * std::max({(size_t)P.ipc_solve * P.state_doubles_solve,
                                                          (size_t)P.ipc_sens * P.state_doubles_sens,
                                                          (size_t)P.ipc_adj * P.state_doubles_adj}) * 8 + 64))

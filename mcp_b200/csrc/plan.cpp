@@ -17,7 +17,7 @@ namespace {
 constexpr int kMaxWindowRows = 256;     // pivot key keeps the slot in 8 bits (kernel_template.cuh)
 constexpr int kMaxSensRhs = 16;
 constexpr int kSmemBudget = 227 * 1024; // bytes per CTA on sm_100a
-constexpr int kAsmChunk = 200;        // terms per chunk of the two-phase assembly (sizes the shared term buffer)
+constexpr int kAsmChunk = 96;         // terms per chunk of the two-phase assembly (sizes the shared term buffer)
 constexpr int kThetaSmemMax = 512;      // θ longer than this is read from global memory in place
 
 bool is_binary(int op) { return op >= MCPB200_OP_ADD && op <= MCPB200_OP_DIV; }
@@ -1129,39 +1129,52 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     pw = (((P.WC + 1 + npart - 1) / npart) + 1) & ~1;
     return P.regwin && rs <= P.sub && pw <= regwin_pw_max;
   };
+  // The window kernels keep the G rows in `sol` (the evaluation writes row i to position iperm[i], the condensed
+  // right-hand side is then formed in place), so G needs no storage of its own: with the back substitution off the
+  // shared-memory ring (r2) the window region shrinks to the assembly's term buffer, and more instances fit an SM.
+  const bool g_on_sol = !P.dense_schur && !P.dense_kernel && !P.tiny_kernel;
   auto window_doubles = [&](int ws, int nrhs) -> int64_t {
     int npart, pw;
     const bool regwin = regwin_geom(npart, pw);
     const int es = (pw * npart + nrhs + 3) & ~1;
     if (!regwin) return (int64_t)P.R * ws + even(P.R) + 4;                 // + mailbox of the cooperative sweep (NWIDE)
     int64_t w = 3 * (int64_t)es;                                           // published pivot row + 2 staging rows
-    w = std::max<int64_t>(w, std::min<int64_t>(8, N) * uts);               // ring depth up to 8
     w = std::max<int64_t>(w, std::min<int64_t>(nterms_all, kAsmChunk));     // two-phase assembly buffer (chunked)
-    if (nx <= 1024) w = std::max<int64_t>(w, nx);                          // G alias
+    if (!g_on_sol && nx <= 1024) w = std::max<int64_t>(w, nx);             // G alias (plans that do not keep G in `sol`)
     return w;
   };
   const int64_t win_solve = window_doubles(P.WS1, 1);
   int64_t win_sens = window_doubles(P.WSS, P.nrhs_sens);
   // G is consumed (residual norm, condensed rhs) before the window is used, so it shares the window's
   // storage whenever it fits; H[k] is consumed by the very lane/iteration that writes w[k], so H lives in w.
-  const bool g_alias = win_solve >= nx;
-  place("SOLVE_OFF_X", nx);
-  place("SOLVE_OFF_Y", ny);
-  place("SOLVE_OFF_S", ny);
-  if (!g_alias) place("SOLVE_OFF_G", nx);
-  place("SOLVE_OFF_JV", njv);
-  place("SOLVE_OFF_DINV", ny);
-  lay << "#define SOLVE_OFF_H " << off << "\n";
-  place("SOLVE_OFF_W", ny);
-  place("SOLVE_OFF_SOL", N);
-  if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
+  const bool g_alias = !g_on_sol && win_solve >= nx;
+  // `s` is only ever read and written in lane-strided sweeps (residual, recovery of δs, linesearch, update): it can live
+  // in a per-instance global block (coalesced, L1/L2-resident) when that buys resident instances (decided below).
+  int s_global = 0;
+  int64_t solve_state = 0, solve_doubles = 0;
+  auto layout_solve = [&]() {
+    off = 0;
+    place("SOLVE_OFF_X", nx);
+    place("SOLVE_OFF_Y", ny);
+    if (!s_global) place("SOLVE_OFF_S", ny);
+    else lay << "#undef SOLVE_OFF_S\n#define SOLVE_OFF_S 0\n";
+    if (!g_alias && !g_on_sol) place("SOLVE_OFF_G", nx);
+    place("SOLVE_OFF_JV", njv);
+    place("SOLVE_OFF_DINV", ny);
+    lay << "#undef SOLVE_OFF_H\n#define SOLVE_OFF_H " << off << "\n";
+    place("SOLVE_OFF_W", ny);
+    place("SOLVE_OFF_SOL", N);
+    if (P.theta_in_smem) place("SOLVE_OFF_TH", nt);
+    place("SOLVE_OFF_STAGE", P.dense_schur ? 2 * even(N) : 0);
+    solve_state = off;     // everything above is "state"; the window region follows
+    if (g_alias || g_on_sol) lay << "#undef SOLVE_OFF_G\n#define SOLVE_OFF_G 0\n";
+    lay << "#undef SOLVE_G_IN_WIN\n#define SOLVE_G_IN_WIN " << (g_alias ? 1 : 0) << "\n#undef SOLVE_G_ON_SOL\n#define SOLVE_G_ON_SOL "
+        << (g_on_sol ? 1 : 0) << "\n";
+    place("SOLVE_OFF_WIN", win_solve);
+    solve_doubles = off;
+  };
+  layout_solve();
   const int64_t stage_n = even(N);
-  place("SOLVE_OFF_STAGE", P.dense_schur ? 2 * stage_n : 0);
-  const int64_t solve_state = off;     // everything above is "state"; the window region follows
-  if (g_alias) lay << "#define SOLVE_OFF_G 0\n";
-  lay << "#define SOLVE_G_IN_WIN " << (g_alias ? 1 : 0) << "\n";
-  place("SOLVE_OFF_WIN", win_solve);
-  int64_t solve_doubles = off;
   int64_t sens_state = 0, sens_doubles = 0;
   auto layout_sens = [&]() {
     off = 0;
@@ -1217,6 +1230,20 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       layout_sens();
     }
   }
+  // Resident warps come in fours (one register file per scheduler: 17 warps cost the registers of 20), so above 16 only
+  // multiples of 4 are used; `s` moves to the global block when that reaches the next multiple.  MCPB200_S_GLOBAL overrides.
+  auto quad = [](int w) { return w > 16 ? (w / 4) * 4 : w; };
+  if (!P.large_state && !P.dense_kernel && !P.tiny_kernel && !P.dense_schur && P.sub == 32 && ny > 0) {
+    int npart, pw;
+    if (regwin_geom(npart, pw)) {
+      s_global = quad(warps_for(solve_doubles - even(ny))) > quad(warps_for(solve_doubles)) ? 1 : 0;
+      if (const char* e = getenv("MCPB200_S_GLOBAL")) s_global = atoi(e) != 0;
+      if (s_global) {
+        layout_solve();
+        P.state_doubles_solve = even(ny) + 2;
+      }
+    }
+  }
   int sol_in_smem = 0;
   if (P.large_state) {
     solve_doubles = even(win_solve);
@@ -1239,6 +1266,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     P.state_doubles_sens = even(sens_state) + 2;
   }
   P.ipc_solve = warps_for(solve_doubles);
+  if (!P.large_state && !P.dense_kernel && !P.tiny_kernel && P.sub == 32) P.ipc_solve = quad(P.ipc_solve);
   P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
   if (P.large_state) {
     P.ipc_solve = std::min(P.ipc_solve, ls_cap);
@@ -1445,7 +1473,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     os << "#define RING_D " << std::max<int64_t>(2, std::min<int64_t>(8, std::min(win1, wins) / uts)) << "\n";
   }
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
-  os << "#define FULL_Y " << P.full_y << "\n";
+  os << "#define FULL_Y " << P.full_y << "\n#define S_GLOBAL " << s_global << "\n";
   os << "#define TINY_KERNEL " << P.tiny_kernel << "\n";
   os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n#define REGWIN_PW_MAX " << regwin_pw_max << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
@@ -1544,7 +1572,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (const char* e = getenv("MCPB200_SHAPES")) use_shapes = atoi(e) != 0;
   if (P.dense_kernel < 2) {
     std::vector<Emitter::OutT> outs;
-    for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], 0, i});
+    for (int i = 0; i < nx; ++i) outs.push_back({P.gh_nodes[i], 0, g_on_sol ? P.iperm[i] : i});   // G row i → sol[iperm[i]]
     for (int i = 0; i < ny; ++i) outs.push_back({P.gh_nodes[nx + i], 1, i});
     for (int i = 0; i < njv; ++i) outs.push_back({P.jv_nodes[i], 2, i});
     E.evaluation(os, "mcp_eval_newton",
