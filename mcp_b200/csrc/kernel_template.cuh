@@ -116,10 +116,21 @@ __device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, F
 // (first dest of each condensed row) and CPOS_S[ND] (circular window position of each dest).
 // ------------------------------------------------------------------------------------------------
 // Geometry of the register-resident window (see band_solve): NPART lanes per window row, PW positions each.
-// WR + 1 row slots: the spare one lets the row that enters the window be staged a whole pivot step before it is needed.
-#define BS_RS (WR + 1)
+// BS_SPARE = 1: WR + 1 row slots — the spare one lets the row that enters the window be staged a whole pivot step before it
+// is needed (takes the staging round trip off the pivot chain).  Measured neutral on the lane-change game, and it costs a
+// fourth quarter-warp of broadcast loads (26 instead of 24 active lanes), so the plans emit BS_SPARE = 0.
+#ifndef BS_SPARE
+#define BS_SPARE 0
+#endif
+#ifndef BS_PRED_ACTIVE
+#define BS_PRED_ACTIVE 2   // 0: every lane loads the pivot row; 1: branch around idle lanes (measured −8 %); 2: predicated loads (+3 %)
+#endif
+#ifndef BS_PIV_FROM_U
+#define BS_PIV_FROM_U 1    // pivot from the broadcast load + one multiplier shuffle, instead of two shuffles
+#endif
+#define BS_RS (WR + BS_SPARE)
 #define BS_NPART ((BS_RS <= SUB) ? ((SUB / BS_RS) >= 4 ? 4 : ((SUB / BS_RS) >= 2 ? 2 : 1)) : 1)
-#define BS_PW ((((WC + 1 + BS_NPART - 1) / BS_NPART) + 1) & ~1)
+#define BS_PW ((((WC + BS_SPARE + BS_NPART - 1) / BS_NPART) + 1) & ~1)
 #define BS_REGWIN (REGWIN && BS_RS <= SUB && BS_PW <= REGWIN_PW_MAX)
 #define BS_PREFETCH_AT ((NRED > 8) ? 8 : 1)   // pivot steps before the end of the factorisation at which Uᵀ is prefetched into the L2
 
@@ -145,12 +156,14 @@ __device__ __forceinline__ void load_shared_tables(double* smem_base, bool trans
   // Rows 0 … WR are in the initial window (relative to column 0); row r > WR is staged at the end of pivot step
   // r − WR − 1, relative to column r − WR, one step before its first column (r − WR + 1 = r − KL) is eliminated: its
   // positions are 1 … WC.  Row WR itself sits at positions 1 … WC of the initial window.
+  // (without the spare slot: rows 0 … WR−1 initial, row r ≥ WR staged at the end of step r − WR relative to column
+  // r − WR + 1 = r − KL, positions 0 … WC−1)
   for (int r = threadIdx.x; r < NRED; r += blockDim.x) {
-    const int first = (r > WR) ? (r - WR) % WC : 0;
+    const int first = (r >= BS_RS) ? (r - BS_RS + 1) % WC : 0;
     for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
       int d = (int)cpos[e] - first;
       if (d < 0) d += WC;
-      if (r >= WR && d == 0) d = WC;   // (col mod WC cannot tell WC from 0; these rows have no entry at position 0)
+      if (BS_SPARE && r >= WR && d == 0) d = WC;   // (col mod WC cannot tell WC from 0; these rows have no entry at position 0)
       cpos[e] = (unsigned short)d;
     }
   }
@@ -377,6 +390,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     double* Eb = E;
     double* Eo = E + ES;
     int left = NRED;                               // NRED − j
+#if BS_PRED_ACTIVE == 2
+    double u[PW + 2];
+#pragma unroll
+    for (int i = 0; i < PW + 2; ++i) u[i] = 0.0;
+#endif
 #pragma unroll 1
     for (; left > 0; --left) {
       if (left == BS_PREFETCH_AT) {
@@ -414,7 +432,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         double2* dst = reinterpret_cast<double2*>(Pb + part * PW);
 #pragma unroll
         for (int k = 0; k < PW / 2; ++k) dst[k] = make_double2(a[2 * k], a[2 * k + 1]);
-        if (part == 0) {
+        if (part == NPART - 1) {   // the right-hand sides ride with the row's LAST part: Pb[WCP] is the pair it loads anyway
 #pragma unroll
           for (int q = 0; q < NRHS; ++q) {
             Pb[WCP + q] = rh[q];
@@ -424,21 +442,35 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
       }
       __syncwarp(smask);
       // ---- broadcast loads of the pivot row (in flight while the multipliers are computed) ------------------
-      double u[PW + 2], urh[NRHS];
-      {
+      // Only the lanes that hold window rows load (the idle quarter-warp costs no shared-memory wavefronts).
+#if BS_PRED_ACTIVE != 2
+      double u[PW + 2];   // the pivot row as seen by my part
+#endif
+      double urh[NRHS];
+      double piv = 1.0;
+      if (BS_PRED_ACTIVE != 1 || active) {   // BS_PRED_ACTIVE == 1: only the lanes that hold rows load and update (a branch)
+#if BS_PRED_ACTIVE == 2
+        // predicated (not branched) 128-bit loads: the idle quarter-warp issues no shared-memory wavefronts, the warp
+        // stays converged; u is loop-carried (idle lanes keep the zeros it was initialised with)
+        const unsigned ua = (unsigned)__cvta_generic_to_shared(Pb + part * PW);
+        const int act = active ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k <= PW / 2; ++k)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.shared.v2.f64 {%0, %1}, [%3];\n\t}"
+                       : "+d"(u[2 * k]), "+d"(u[2 * k + 1]) : "r"(act), "r"(ua + 16u * k) : "memory");
+#else
         const double2* up = reinterpret_cast<const double2*>(Pb + part * PW);
 #pragma unroll
         for (int k = 0; k <= PW / 2; ++k) {  // PW/2 + 1 aligned pairs: my part and the first entry of the next
-#ifdef EXP_NO_UBCAST
-          const double2 v = make_double2(1.0 + k, 2.0);
-#else
           const double2 v = up[k];
-#endif
           u[2 * k] = v.x;
           u[2 * k + 1] = v.y;
         }
+#endif
+        urh[0] = u[PW];   // last part: Pb[WCP], the pivot row's first right-hand side (other parts never publish theirs)
 #pragma unroll
-        for (int q = 0; q < NRHS; ++q) urh[q] = Pb[WCP + q];
+        for (int q = 1; q < NRHS; ++q) urh[q] = Pb[WCP + q];
+        piv = u[0];       // part-0 lanes: Pb[0], the pivot itself (the other parts never use their rp)
       }
       double ut_out[CPW];
 #pragma unroll
@@ -447,9 +479,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         ut_out[k] = (t < WC) ? Pb[t] : 0.0;
       }
       // ---- pivot, reciprocal, multipliers --------------------------------------------------------------------
-      const double piv = __shfl_sync(smask, head, p * NPART, SUB);
-      double a0row = head;
-      if constexpr (NPART > 1) a0row = __shfl_sync(smask, head, sl - part, SUB);   // my row's entry in the pivot column
+      // (the multiplier is formed by the row's part-0 lane, which holds the pivot-column entry, and handed to the other
+      // parts with ONE shuffle — shuffles share the shared-memory data pipe, which is what bounds this loop)
+#if !BS_PIV_FROM_U
+      piv = __shfl_sync(smask, head, p * NPART, SUB);
+#endif
       double rp;
       asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rp) : "d"(piv));   // ~20 bits, then two Newton steps: ≤ 1 ulp
       {
@@ -458,7 +492,14 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         er = fma(-piv, rp, 1.0);
         rp = fma(rp, er, rp);
       }
+#if BS_PIV_FROM_U
+      double m = (active && !mine) ? -(head * rp) : 0.0;
+      if constexpr (NPART > 1) m = __shfl_sync(smask, m, sl - part, SUB);
+#else
+      double a0row = head;
+      if constexpr (NPART > 1) a0row = __shfl_sync(smask, head, sl - part, SUB);   // my row's entry in the pivot column
       const double m = (active && !mine) ? -(a0row * rp) : 0.0;
+#endif
       double nx = 0.0;
       if constexpr (NPART > 1) {
         nx = __shfl_sync(smask, a[0], (sl + 1) % SUB, SUB);     // first entry of my row's next part
@@ -473,11 +514,13 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
 #endif
       }
       // ---- eliminate column j and slide the window: a[i] ← a[i+1] − m·u[i+1] ------------------------------
+      if (BS_PRED_ACTIVE != 1 || active) {
 #pragma unroll
-      for (int i = 0; i + 1 < PW; ++i) a[i] = fma(m, u[i + 1], a[i + 1]);
-      a[PW - 1] = (part == NPART - 1) ? 0.0 : fma(m, u[PW], nx);   // last part: column j+WCP enters, zero
+        for (int i = 0; i + 1 < PW; ++i) a[i] = fma(m, u[i + 1], a[i + 1]);
+        a[PW - 1] = (part == NPART - 1) ? 0.0 : fma(m, u[PW], nx);   // last part: column j+WCP enters, zero
 #pragma unroll
-      for (int q = 0; q < NRHS; ++q) rh[q] = fma(m, urh[q], rh[q]);
+        for (int q = 0; q < NRHS; ++q) rh[q] = fma(m, urh[q], rh[q]);
+      }
       head = a[0];
       // ---- the next row (relative to column j+1, first needed at step j+2) takes over the retired row's lanes ----
 #pragma unroll
@@ -494,7 +537,7 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         }
 #pragma unroll
         for (int q = 0; q < NRHS; ++q) rh[q] = entering ? solj[q * NRED + BS_RS] : 0.0;
-        head = 0.0;   // structurally zero in column j+1: the search and the multipliers need not wait for the reload
+        head = BS_SPARE ? 0.0 : a[0];   // with the spare slot: structurally zero in column j+1, nothing waits for the reload
       }
       e_lo = e_hi;
       if (entering) ++rpj;

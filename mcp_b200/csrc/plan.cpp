@@ -1124,9 +1124,10 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   // slots (one spare, so the entering row is staged a step early), NPART lanes per row, PW positions per lane covering
   // WC + 1 relative columns.
   auto regwin_geom = [&](int& npart, int& pw) -> bool {
-    const int rs = P.R + 1;
+    const int spare = 0;   // BS_SPARE of the kernel template (the spare row slot was measured neutral and costs lanes)
+    const int rs = P.R + spare;
     npart = (rs <= P.sub) ? ((P.sub / rs) >= 4 ? 4 : ((P.sub / rs) >= 2 ? 2 : 1)) : 1;
-    pw = (((P.WC + 1 + npart - 1) / npart) + 1) & ~1;
+    pw = (((P.WC + spare + npart - 1) / npart) + 1) & ~1;
     return P.regwin && rs <= P.sub && pw <= regwin_pw_max;
   };
   // The window kernels keep the G rows in `sol` (the evaluation writes row i to position iperm[i], the condensed
@@ -1236,7 +1237,11 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   if (!P.large_state && !P.dense_kernel && !P.tiny_kernel && !P.dense_schur && P.sub == 32 && ny > 0) {
     int npart, pw;
     if (regwin_geom(npart, pw)) {
-      s_global = quad(warps_for(solve_doubles - even(ny))) > quad(warps_for(solve_doubles)) ? 1 : 0;
+      // Measured on the lane-change game (bench, converged solves/s): 20 instances at 96 registers 219.8–227.1 k, 16
+      // instances at 128 registers 230.6–237.3 k — the pivot loop spills at 96, and the SM is bound by its shared-memory
+      // data pipe, not by the number of resident warps.  So the move is opt-in: MCPB200_S_GLOBAL=1.
+      (void)quad(warps_for(solve_doubles - even(ny)));
+      s_global = 0;
       if (const char* e = getenv("MCPB200_S_GLOBAL")) s_global = atoi(e) != 0;
       if (s_global) {
         layout_solve();
