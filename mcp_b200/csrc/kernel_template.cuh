@@ -125,6 +125,9 @@ __device__ __forceinline__ double warp_nanmax(double v) { return sub_nanmax(v, F
 #ifndef BS_PRED_ACTIVE
 #define BS_PRED_ACTIVE 2   // 0: every lane loads the pivot row; 1: branch around idle lanes (measured −8 %); 2: predicated loads (+3 %)
 #endif
+#ifndef BS_SELF_CLEAR
+#define BS_SELF_CLEAR 0    // (measured −6 % in the bench) staging rows cleared by the lanes that wrote them (one wavefront) instead of zero-filled per step (two)
+#endif
 #ifndef BS_PIV_FROM_U
 #define BS_PIV_FROM_U 1    // pivot from the broadcast load + one multiplier shuffle, instead of two shuffles
 #endif
@@ -389,6 +392,11 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
     double* solj = sol;                            // → sol[j]; the staged row's right-hand side is solj[BS_RS]
     double* Eb = E;
     double* Eo = E + ES;
+    for (int q = sl; q < 2 * ES; q += SUB) E[q] = 0.0;   // both staging rows start (and are kept) all-zero
+    int zrel[CPW];
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) zrel[k] = -1;
+    __syncwarp(smask);
     int left = NRED;                               // NRED − j
 #if BS_PRED_ACTIVE == 2
     double u[PW + 2];
@@ -417,7 +425,9 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
           prel[k] = cpos[e];
         }
       }
+#if !BS_SELF_CLEAR
       for (int q = sl; q < ES; q += SUB) Eb[q] = 0.0;   // (this buffer was last read two steps ago)
+#endif
       // ---- pivot search over column j: max |head| on a 12-bit-truncated mantissa, row in the low byte ----
       unsigned key = 0;
       if (lane_pub) key = ((unsigned)__double2hiint(fabs(head)) & 0xffffff00u) | (unsigned)(255 - row);
@@ -441,6 +451,13 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         }
       }
       __syncwarp(smask);
+      // the staging row of the PREVIOUS step has been consumed (its reload precedes the barrier above): the lanes that
+      // scattered into it clear their entries, so both staging rows are all-zero whenever they are scattered into
+#if BS_SELF_CLEAR
+#pragma unroll
+      for (int k = 0; k < CPW; ++k)
+        if (zrel[k] >= 0) Eo[zrel[k]] = 0.0;
+#endif
       // ---- broadcast loads of the pivot row (in flight while the multipliers are computed) ------------------
       // Only the lanes that hold window rows load (the idle quarter-warp costs no shared-memory wavefronts).
 #if BS_PRED_ACTIVE != 2
@@ -539,6 +556,10 @@ __device__ int band_solve(double* RS W, const double* RS Cval, double* RS UT,
         for (int q = 0; q < NRHS; ++q) rh[q] = entering ? solj[q * NRED + BS_RS] : 0.0;
         head = BS_SPARE ? 0.0 : a[0];   // with the spare slot: structurally zero in column j+1, nothing waits for the reload
       }
+#if BS_SELF_CLEAR
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) zrel[k] = prel[k];
+#endif
       e_lo = e_hi;
       if (entering) ++rpj;
       UTj += UTS;
@@ -2154,9 +2175,13 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
   // Pass 0 therefore runs every instance only up to `step_budget` steps (checked at outer-iteration
   // boundaries, where the whole solver state is (x, y, s, ϵ, kkt_error, outer_iters)), parks the rest in
   // the output arrays and a deferred list; pass 1 (a second launch) resumes them, all long, together.
+  // r2: pass 1 runs them in SLICES of `step_budget` steps too and re-queues an unfinished instance at the end of the same
+  // list, so the work stays evenly spread over the slots until the very end: with whole instances (≈ 870 steps each,
+  // ≈ 5 per slot for the bench batch) the last round ran at half occupancy on average — pass 1 ran at 84 % of pass 0's
+  // Newton-step rate.  List slots ≥ n_deferred are filled during the pass (−1 = not yet): a slot whose sub-warp has
+  // claimed such an entry polls it; everyone leaves when all n_deferred instances have finished.
   const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
-  const bool spread = p.pass && n_deferred <= (unsigned long long)gridDim.x * SOLVE_INST;
-  bool fetched = false;
+  int steps_entry = 0;
 
   // solver state of my sub-warp's instance (replicated in each of its lanes)
   bool have = false, done = false, head = true, brk = false;
@@ -2170,19 +2195,31 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
     while (!done && !step) {
       if (!have) {
         unsigned long long q = 0;
-        if (spread) {   // pass 1 with fewer instances than slots: one per SM first (each is a long, latency-bound run)
-          q = fetched ? n_deferred : (unsigned long long)blockIdx.x + (unsigned long long)gridDim.x * slot;
-          fetched = true;
-        } else {
-          if (sl == 0) q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
-          q = __shfl_sync(smask, q, 0, SUB);
-        }
+        if (sl == 0) q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+        q = __shfl_sync(smask, q, 0, SUB);
         if (p.pass) {
-          if (q >= n_deferred) {
+          long long got = -1;
+          if (q < n_deferred) {
+            got = p.deferred[q];
+          } else {
+            // an entry that is (or may still be) produced during this pass
+            if (sl == 0) {
+              const long long t0 = clock64();
+              for (;;) {
+                got = *reinterpret_cast<volatile int*>(p.deferred + q);
+                if (got >= 0) break;
+                if (*reinterpret_cast<volatile unsigned long long*>(p.counters + 6) >= n_deferred) break;   // all finished
+                if (clock64() - t0 > 20000000000LL) break;   // (≈ 10 s: never hang the device on a logic error)
+                __nanosleep(1000);
+              }
+            }
+            got = __shfl_sync(smask, got, 0, SUB);
+          }
+          if (got < 0) {
             done = true;
             break;
           }
-          inst = (unsigned long long)p.deferred[q];
+          inst = (unsigned long long)got;
         } else {
           if (q >= (unsigned long long)p.B) {
             done = true;
@@ -2201,16 +2238,16 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
         status = 0;                                        // :69
         outer = 1;                                         // :70
         steps = 0;
-        if (p.pass) {
-          for (int i = sl; i < NX; i += SUB) x[i] = p.x_out[inst * NX + i];
+        if (p.pass) {   // (L2 loads: the state may have been parked by another SM during this very launch)
+          for (int i = sl; i < NX; i += SUB) x[i] = __ldcg(p.x_out + inst * NX + i);
           for (int i = sl; i < NY; i += SUB) {
-            y[i] = p.y_out[inst * NY + i];
-            s[i] = p.s_out[inst * NY + i];
+            y[i] = __ldcg(p.y_out + inst * NY + i);
+            s[i] = __ldcg(p.s_out + inst * NY + i);
           }
-          eps = p.eps_out[inst];
-          kkt = p.kkt_out[inst];
-          outer = p.outer_out[inst];
-          steps = p.steps_out[inst];
+          eps = __ldcg(p.eps_out + inst);
+          kkt = __ldcg(p.kkt_out + inst);
+          outer = __ldcg(p.outer_out + inst);
+          steps = __ldcg(p.steps_out + inst);
         } else {
           for (int i = sl; i < NX; i += SUB) x[i] = p.x0 ? p.x0[inst * NX + i] : 0.0;
           for (int i = sl; i < NY; i += SUB) {
@@ -2219,6 +2256,7 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
           }
         }
         __syncwarp(smask);
+        steps_entry = steps;
         have = true;
         head = true;
         brk = false;
@@ -2229,7 +2267,7 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
 #else
         const bool go = kkt > tol && eps > tol && outer < p.max_outer;
 #endif
-        const bool park = go && p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget;
+        const bool park = go && p.step_budget > 0 && steps - steps_entry >= p.step_budget;
         if (!go || park) {
           if (!park && outer == p.max_outer) status = 1;  // :117-119
           for (int i = sl; i < NX; i += SUB) p.x_out[inst * NX + i] = x[i];
@@ -2243,11 +2281,25 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
             p.outer_out[inst] = outer;
             p.status_out[inst] = status;
             p.steps_out[inst] = steps;
-            if (park) {
+          }
+          if (park && p.pass) __threadfence();   // every lane's part of the parked state, before the entry is published
+          __syncwarp(smask);
+          if (sl == 0) {
+            if (park && p.pass == 0) {
               p.deferred[atomicAdd(p.counters + 3, 1ULL)] = (int)inst;
+            } else if (park) {
+              // re-queue behind everything already in the list; the parked state must be visible device-wide before
+              // the entry is
+              __threadfence();
+              const unsigned long long slot_q = n_deferred + atomicAdd(p.counters + 5, 1ULL);
+              atomicExch(p.deferred + slot_q, (int)inst);
             } else {
               atomicAdd(p.counters + 1, (unsigned long long)steps);
               if (status == 0) atomicAdd(p.counters + 2, 1ULL);
+              if (p.pass) {
+                __threadfence();
+                atomicAdd(p.counters + 6, 1ULL);
+              }
             }
           }
           __syncwarp(smask);

@@ -564,7 +564,12 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   // resumes them together.  MCPB200_PASS1_STEPS overrides the budget (0 disables the second pass).
   int budget = 2 * std::max(p.max_inner, 1) + 24;
   if (const char* e = getenv("MCPB200_PASS1_STEPS")) budget = atoi(e);
-  if (st->deferred.ensure((size_t)p.B * 4 + 16)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(deferred) failed");
+  // deferred list: the window kernels re-queue unfinished instances during pass 1 (slices of `budget` steps; at most
+  // (max_outer·max_inner)/budget + 1 entries per instance), entries not yet produced read −1
+  const bool requeue = !P.tiny_kernel && !P.dense_kernel && budget > 0;
+  const size_t slices = requeue ? (size_t)std::max(1, p.max_outer) * (size_t)std::max(1, p.max_inner) / (size_t)budget + 2 : 1;
+  const size_t deferred_bytes = (size_t)p.B * 4 * slices + 16;
+  if (st->deferred.ensure(deferred_bytes)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(deferred) failed");
   p.deferred = (int*)st->deferred.p;
   if (!p.steps_out) {
     if (st->steps_tmp.ensure((size_t)p.B * 4 + 16)) return set_err(h, MCPB200_ERR_CUDA, "cudaMalloc(steps) failed");
@@ -575,6 +580,7 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   // another stream (e.g. torch's, by the _device entry points) must finish before this one may reuse them.
   if (st->pending) CUDA_TRY(h, cudaStreamWaitEvent(stream, st->ev1, 0));
   CUDA_TRY(h, cudaMemsetAsync(st->counters.p, 0, 64, stream));
+  if (requeue) CUDA_TRY(h, cudaMemsetAsync(st->deferred.p, 0xff, deferred_bytes, stream));
   CUDA_TRY(h, cudaEventRecord(st->ev0, stream));
   void* args[] = {&p};
   p.pass = 0;
@@ -584,6 +590,10 @@ int launch_solve(mcpb200_problem* h, DeviceState* st, SolveParams& p, cudaStream
   if (budget > 0) {
     CUDA_TRY(h, cudaEventRecord(st->ev_mid, stream));
     p.pass = 1;
+    if (const char* e = getenv("MCPB200_REQUEUE")) {   // A/B: 0 = pass 1 runs every deferred instance to its end in one go
+      if (atoi(e) == 0) p.step_budget = 0;
+      else p.step_budget = atoi(e);                    // or the slice length in Newton steps
+    }
     CU_TRY(h, driver().LaunchKernel(st->f_solve, grid, 1, 1, block, 1, 1, smem_bytes, (CUstream)stream, args, nullptr));
     st->launches = 2;
   }
