@@ -175,11 +175,19 @@ function solve(::InteriorPoint, mcp::PrimalDualMCP, Θ::AbstractMatrix{<:Real}; 
     _solve_batched(mcp, Matrix{Float64}(Θ), dense(X₀), dense(Y₀), dense(S₀), opts)
 end
 
-"`solve(InteriorPoint(), mcp, θ; x₀, y₀, s₀, …)` — src/solver.jl:35-122; returns the same NamedTuple (src/solver.jl:121)."
+"""
+`solve(InteriorPoint(), mcp, θ; x₀, y₀, s₀, …)` — src/solver.jl:35-122; returns the same NamedTuple (src/solver.jl:121).
+
+Like the reference, which sets `x = x₀` and updates it in place (src/solver.jl:64-66,103-105), the returned `x`, `y`, `s`
+ALIAS the caller's `x₀`, `y₀`, `s₀` whenever those are mutable `Vector{Float64}`s: the solution is written back into
+them and they are what the NamedTuple holds.  (Other array types — ranges, views, non-Float64 — are left untouched and
+fresh vectors are returned, where the reference would have thrown on the in-place update.)
+"""
 function solve(ip::InteriorPoint, mcp::PrimalDualMCP, θ::AbstractVector{<:Real}; x₀ = nothing, y₀ = nothing, s₀ = nothing, kwargs...)
     col(v) = v === nothing ? nothing : reshape(collect(Float64, v), :, 1)
     r = solve(ip, mcp, reshape(collect(Float64, θ), :, 1); X₀ = col(x₀), Y₀ = col(y₀), S₀ = col(s₀), kwargs...)
-    (; status = r.status[1] == 0 ? :solved : :failed, x = r.x[:, 1], y = r.y[:, 1], s = r.s[:, 1],
+    alias(v₀, v) = v₀ isa Vector{Float64} ? copyto!(v₀, v) : v
+    (; status = r.status[1] == 0 ? :solved : :failed, x = alias(x₀, r.x[:, 1]), y = alias(y₀, r.y[:, 1]), s = alias(s₀, r.s[:, 1]),
        kkt_error = r.kkt_error[1], ϵ = r.ϵ[1], outer_iters = Int(r.outer_iters[1]))
 end
 

@@ -7,7 +7,12 @@ PARITY PIN STATUS: the Julia reference cannot run in this image (no `julia`), an
 hold no stored vectors — only analytic assertions (`/root/reference/test/runtests.jl:30-38,80-84,
 112-115`).  Those known answers are checked in `tests/test_oracle.py`; beyond them (1e-6 agreement on
 lane-change / QP100) the parity is **unpinned by the reference** and rests on this restatement being
-line-by-line faithful.  Every block below cites the line it restates.
+line-by-line faithful.  Every block below cites the line it restates.  What round 2 added to shrink that
+gap (none of it can replace a Julia run): the PROBLEMS this loop is run on are pinned independently of the
+product's tracer (`oracle/independent_problems.py`, `tests/test_independent_definitions.py`: F, ∇F_z, ∇F_θ of
+the lane-change and masked games equal a second, autograd-based restatement of the reference's sources to
+1e-9), and the LOOP's floating-point trajectory is checked against an extended-precision run of the same loop on
+the full KKT system (`oracle/ip_oracle_ext.py`; `profiles/r2_adjudicate_*.json`).
 
 Third-party arithmetic the reference delegates to (not under /root/reference):
 * UMFPACK sparse LU via LinearSolve.jl ≥2.38 (`src/solver.jl:50,61,83`)  → here SuperLU (`splu`),
