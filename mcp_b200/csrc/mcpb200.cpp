@@ -400,6 +400,8 @@ std::string nvrtc_to_cubin(const std::string& src, const std::string& name, bool
   return n ? std::string() : std::string("NVRTC produced an empty cubin");
 }
 
+constexpr uint32_t MCPB200_NO_CACHE_READ_INTERNAL = 0x40000000u;   // (internal) recompile and overwrite the cache entry
+
 int compile_source(mcpb200_problem* h, uint32_t flags) {
   const std::string& src = h->plan.source;
   const std::vector<std::string>& units = h->plan.units;
@@ -414,7 +416,7 @@ int compile_source(mcpb200_problem* h, uint32_t flags) {
   const std::string cu_path = dir + "/mcp_" + key + ".cu";
   const std::string bin_path = dir + "/mcp_" + key + ".cubin";
   const bool use_cache = !(flags & MCPB200_NO_CACHE);
-  if (use_cache && read_file(bin_path, h->cubin)) {
+  if (use_cache && !(flags & MCPB200_NO_CACHE_READ_INTERNAL) && read_file(bin_path, h->cubin)) {
     h->cache_hit = true;
     return MCPB200_OK;
   }
@@ -505,7 +507,18 @@ int device_state(mcpb200_problem* h, int dev, DeviceState** out) {
     if (prop.major != 10)
       return set_err(h, MCPB200_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100: this library targets B200 only");
     st->num_sms = prop.multiProcessorCount;
-    CU_TRY(h, D.ModuleLoadData(&st->mod, h->cubin.data()));
+    {
+      CUresult r = D.ModuleLoadData(&st->mod, h->cubin.data());
+      if (r != CUDA_SUCCESS && h->cache_hit) {
+        // a corrupt or stale cubin in the on-disk cache: compile afresh once (which overwrites the cache entry)
+        h->cache_hit = false;
+        h->cubin.clear();
+        const int rc = compile_source(h, MCPB200_NO_CACHE_READ_INTERNAL);
+        if (rc) return rc;
+        r = D.ModuleLoadData(&st->mod, h->cubin.data());
+      }
+      if (r != CUDA_SUCCESS) return set_err(h, MCPB200_ERR_CUDA, std::string("cuModuleLoadData: ") + cu_err(r));
+    }
     CU_TRY(h, D.ModuleGetFunction(&st->f_solve, st->mod, "mcp_solve_kernel"));
     if (!h->plan.tiny_kernel)
       CU_TRY(h, D.FuncSetAttribute(st->f_solve, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)h->plan.smem_solve));

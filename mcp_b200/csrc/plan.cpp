@@ -196,10 +196,12 @@ std::vector<int> anneal_ordering(int n, const std::vector<std::pair<int, int>>& 
   std::vector<int> best = inv;
   const int bw0 = std::max(kl, ku);
   if (bw0 <= 1) return perm;
-  const long M = std::max<long>(200000, std::min<long>(4000000, 4000L * n));
+  long M = std::max<long>(200000, std::min<long>(4000000, 4000L * n));
+  if (const char* e = getenv("MCPB200_ANNEAL_ITERS")) M = std::max<long>(1000, atol(e));   // experiments
   double T = pw[bw0] * 0.5;
   const double alpha = std::exp(std::log(1e-8) / (double)M);
   uint64_t rng = 0x9E3779B97F4A7C15ULL;
+  if (const char* e = getenv("MCPB200_ANNEAL_SEED")) rng ^= (uint64_t)atoll(e) * 0xD1B54A32D192ED03ULL;   // experiments
   auto next = [&]() {
     rng ^= rng << 13;
     rng ^= rng >> 7;
@@ -1288,6 +1290,8 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     if (!regwin_used && !P.dense_schur) {
       P.nwide = std::max(1, std::min({4, 16 / P.ipc_solve, nbatch}));
       if (const char* e = getenv("MCPB200_NWIDE")) P.nwide = std::max(1, std::min({atoi(e), nbatch, 32 / P.ipc_solve}));
+      // the helpers of instance slot k meet at named barrier 1 + k: ids 1 … 15 exist (0 is __syncthreads)
+      if (P.nwide > 1 && P.ipc_solve > 15) P.nwide = 1;
     }
   }
   if (P.ipc_solve < 1) {
