@@ -1026,6 +1026,235 @@ __device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], cons
   }
 }
 
+// ---- symmetric path (r2) -------------------------------------------------------------------------------------------
+// The condensed matrix of these plans is C = G_x + tol·I + H_xᵀ D⁻¹ H_x (G_y = −H_xᵀ is a plan-time condition of the
+// dense kernels), symmetric whenever G_x is — every QP — and positive definite whenever G_x is positive semi-definite
+// (D⁻¹ > 0 in the interior).  Then the partial-pivoted LU above is replaced by LDLᵀ WITHOUT pivoting, in a layout of
+// its own: lane l owns rows {l, l+32, …} as before, warp w owns the column PAIRS {2w, 2w+1} + 32a, and only the tile
+// blocks on or below the diagonal exist (row chunk b ≥ column block a: 20 doubles per thread for n = 100 instead
+// of 28, in the Schur accumulation too).  One barrier per PANEL of two columns: the diagonal 2×2 block of a panel
+// sits in two lanes of its owner warp (chunk a, lanes 2w and 2w+1 — static register indices), which eliminates
+// column j₀ from column j₁ locally and publishes both straight into Uᵀ (by symmetry row j of U is column j) with the
+// two reciprocal pivots; everybody then applies a rank-2 update (two dependent FMAs per entry, same rounding as
+// column by column).  No pivot search, no pivot-row store→load, finished row chunks and column blocks are skipped
+// statically, and the owner of the NEXT panel updates and factorises it first (look-ahead), so the other warps'
+// trailing updates hide its two reciprocals and the barrier.  The right-hand side (forward substitution) lives in
+// four registers of warp D3P_RW and never crosses warps.  Entries above the diagonal, padding rows and padding
+// columns hold garbage that is never read.
+// Whether G_x is symmetric is checked once per solve on the values (it comes from θ); a pivot that is not positive
+// and finite sends that Newton step — and the rest of the instance — back to the pivoted LU, so nothing the
+// reference solves is lost (src/solver.jl:81-88: UMFPACK factorises any non-singular matrix).  Same Uᵀ / rd layout
+// as the LU, so the back substitution is shared.
+#ifndef D3_SYM
+#define D3_SYM 1
+#endif
+#ifndef D3_SYM_LOOKAHEAD
+#define D3_SYM_LOOKAHEAD 1
+#endif
+#define D3P_RW 15   // warp that carries the right-hand side
+
+__device__ __forceinline__ double d3_rcp(const double d) {
+  double rp;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rp) : "d"(d));   // ~20 bits, then two Newton steps: ≤ 1 ulp
+  double er = fma(-d, rp, 1.0);
+  rp = fma(rp, er, rp);
+  er = fma(-d, rp, 1.0);
+  return fma(rp, er, rp);
+}
+
+// Factorise the panel (columns j0, j0+1) held by the calling warp `wo` in column block A, whose entries are up to
+// date with every earlier panel, and publish it: UT[r·UTLD + j] = entry (r, j) for the rows of chunks ≥ A (rows
+// above the diagonal land in cells nothing reads), rd[j] = 1/d_j — NaN when d_j is not positive and finite.
+template <int A>
+__device__ __forceinline__ void d3p_panel(double (&T)[D3_RCH][D3_RCH][2], const int lane, const int wo, const int j0,
+                                          double* UT, double* rd, const bool lastrow) {
+  constexpr int UTLD = DENSE_UTLD;
+  const bool two = j0 + 1 < NRED;
+  double* q = UT + lane * UTLD + j0;
+#pragma unroll
+  for (int b = A; b < D3_RCH; ++b)
+    if (b < D3_RCH - 1 || lastrow) q[32 * b * UTLD] = T[b][A][0];
+  const double d0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo);
+  const double u0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo + 1);   // U[j0][j0+1]
+  const double rp0 = d3_rcp(d0);
+#pragma unroll
+  for (int b = A; b < D3_RCH; ++b) T[b][A][1] = fma(-(T[b][A][0] * rp0), u0, T[b][A][1]);
+  const double d1 = __shfl_sync(FULLMASK, T[A][A][1], 2 * wo + 1);
+  if (two) {
+#pragma unroll
+    for (int b = A; b < D3_RCH; ++b)
+      if (b < D3_RCH - 1 || lastrow) q[32 * b * UTLD + 1] = T[b][A][1];
+  }
+  const double rp1 = d3_rcp(d1);
+  if (lane == 0) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    rd[j0] = (d0 > 0.0 && d0 <= DBL_MAX_ && rp0 == rp0) ? rp0 : qnan;
+    if (two) rd[j0 + 1] = (d1 > 0.0 && d1 <= DBL_MAX_ && rp1 == rp1) ? rp1 : qnan;
+  }
+}
+
+// rank-2 update of the calling thread's tile block (b ≥ AC, column block AC) with panel (j0, j0+1)
+template <int AC, int AB>
+__device__ __forceinline__ void d3p_update(double (&T)[D3_RCH][D3_RCH][2], const double (&m0)[D3_RCH],
+                                           const double (&m1)[D3_RCH], const double* RS UT, const int wid, const int j0) {
+  constexpr int UTLD = DENSE_UTLD;
+  const int c0 = 32 * AC + 2 * wid;
+  // (only the last column block can run past the matrix: padding columns read the right-hand-side row, finite or
+  // not — their tile entries are never read)
+  const double* q0 = UT + (AC == D3_RCH - 1 ? min(c0, NRED) : c0) * UTLD + j0;
+  const double* q1 = UT + (AC == D3_RCH - 1 ? min(c0 + 1, NRED) : c0 + 1) * UTLD + j0;
+  const double u00 = q0[0], u01 = q0[1], u10 = q1[0], u11 = q1[1];
+#pragma unroll
+  for (int b = (AC > AB ? AC : AB); b < D3_RCH; ++b) {
+    T[b][AC][0] = fma(m1[b], u01, fma(m0[b], u00, T[b][AC][0]));
+    T[b][AC][1] = fma(m1[b], u11, fma(m0[b], u10, T[b][AC][1]));
+  }
+}
+
+// The panels of column block A (columns 32·A … 32·A+31, owner warps 0 … 15 in turn); returns true when a pivot was not
+// positive (the caller falls back to the pivoted LU).
+template <int A>
+__device__ __forceinline__ bool d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], double (&rv)[D3_RCH], const int wid,
+                                           const int lane, double* rd, double* UT, const bool lastrow) {
+  constexpr int UTLD = DENSE_UTLD;
+  if constexpr (A >= D3_RCH) {
+    return false;
+  } else {
+    // my rows' cells of Uᵀ (rows of chunks ≥ A are still live; padding rows read the right-hand-side row)
+    const double* mq = UT + lane * UTLD;
+    const double* mql = UT + min(lane + 32 * (D3_RCH - 1), NRED) * UTLD;
+#pragma unroll 1
+    for (int wo = 0; wo < 16; ++wo) {
+      const int j0 = 32 * A + 2 * wo;
+      if (j0 >= NRED) break;
+      const bool two = j0 + 1 < NRED;
+#if !D3_SYM_LOOKAHEAD
+      if (wid == wo) d3p_panel<A>(T, lane, wo, j0, UT, rd, lastrow);
+#endif
+      __syncthreads();
+      const double rp0 = rd[j0];
+      const double rp1 = two ? rd[j0 + 1] : 0.0;
+      if (!(rp0 == rp0) || !(rp1 == rp1)) return true;
+      double m0[D3_RCH], m1[D3_RCH];
+#pragma unroll
+      for (int b = A; b < D3_RCH; ++b) {
+        const double* q = (b == D3_RCH - 1 ? mql : mq + 32 * b * UTLD) + j0;
+        m0[b] = -(q[0] * rp0);
+        m1[b] = two ? -(q[1] * rp1) : 0.0;
+      }
+      int la = -1;   // column block already updated by the look-ahead
+#if D3_SYM_LOOKAHEAD
+      if (j0 + 2 < NRED) {
+        if (wo < 15) {
+          if (wid == wo + 1) {
+            d3p_update<A, A>(T, m0, m1, UT, wid, j0);
+            d3p_panel<A>(T, lane, wid, j0 + 2, UT, rd, lastrow);
+            la = A;
+          }
+        } else if constexpr (A + 1 < D3_RCH) {
+          if (wid == 0) {
+            d3p_update<A + 1, A>(T, m0, m1, UT, wid, j0);
+            d3p_panel<A + 1>(T, lane, 0, j0 + 2, UT, rd, lastrow);
+            la = A + 1;
+          }
+        }
+      }
+#endif
+      if (wid > wo && la != A) d3p_update<A, A>(T, m0, m1, UT, wid, j0);
+      if constexpr (A + 1 < D3_RCH) { if (la != A + 1) d3p_update<A + 1, A>(T, m0, m1, UT, wid, j0); }
+      if constexpr (A + 2 < D3_RCH) d3p_update<A + 2, A>(T, m0, m1, UT, wid, j0);
+      if constexpr (A + 3 < D3_RCH) d3p_update<A + 3, A>(T, m0, m1, UT, wid, j0);
+      if (wid == D3P_RW) {   // forward substitution of the right-hand side (rows j0, j0+1 are in chunk A, lanes 2wo, 2wo+1)
+        const double r0 = __shfl_sync(FULLMASK, rv[A], 2 * wo);
+        if (lane == 0) UT[NRED * UTLD + j0] = r0;
+#pragma unroll
+        for (int b = A; b < D3_RCH; ++b) rv[b] = fma(m0[b], r0, rv[b]);
+        if (two) {
+          const double r1 = __shfl_sync(FULLMASK, rv[A], 2 * wo + 1);
+          if (lane == 0) UT[NRED * UTLD + j0 + 1] = r1;
+#pragma unroll
+          for (int b = A; b < D3_RCH; ++b) rv[b] = fma(m1[b], r1, rv[b]);
+        }
+      }
+    }
+    return d3p_blocks<A + 1>(T, rv, wid, lane, rd, UT, lastrow);
+  }
+}
+
+// tile of the symmetric layout: the direct part (G_x + tol·I) from the L2-resident block, then + H_xᵀ D⁻¹ H_x, one
+// rank-1 update per constraint from the cached H_x (4 conflict-free + 8 broadcast shared loads per 20 DFMAs)
+__device__ __forceinline__ void d3p_assemble(double (&T)[D3_RCH][D3_RCH][2], const double* Gc, const double* RS Hc,
+                                             const double* RS dinv, const int wid, const int lane) {
+  constexpr int HCS = DENSE_HCS;
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+    for (int a = 0; a <= b; ++a)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = lane + 32 * b, c = 32 * a + 2 * wid + e;
+        T[b][a][e] = (r < NRED && c < NRED) ? __ldcg(Gc + c * D3_GLD + r) : 0.0;
+      }
+  int ri[D3_RCH], ci[D3_RCH];
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b) {
+    ri[b] = min(lane + 32 * b, NRED);   // column NRED of the cached H_x stays 0
+    ci[b] = min(32 * b + 2 * wid, NRED - 1);   // (ci+1 ≤ NRED)
+  }
+#pragma unroll kSchurUnroll
+  for (int k = 0; k < NY; ++k) {
+    const double dk = dinv[k];
+    const double* hr = Hc + k * HCS;
+    double av[D3_RCH], bv[D3_RCH][2];
+#pragma unroll
+    for (int b = 0; b < D3_RCH; ++b) av[b] = hr[ri[b]] * dk;
+#pragma unroll
+    for (int a = 0; a < D3_RCH; ++a) {
+      bv[a][0] = hr[ci[a]];
+      bv[a][1] = hr[ci[a] + 1];
+    }
+#pragma unroll
+    for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+      for (int a = 0; a <= b; ++a) {
+        T[b][a][0] = fma(av[b], bv[a][0], T[b][a][0]);
+        T[b][a][1] = fma(av[b], bv[a][1], T[b][a][1]);
+      }
+  }
+}
+
+// + H_xᵀ D⁻¹ H_x on the register tiles of the LU layout, one rank-1 update per constraint from the cached H_x (4
+// conflict-free + 7 broadcast shared loads per 28 DFMAs)
+__device__ __forceinline__ void d3_schur(double (&acc)[D3_RCH][D3_CPW], const double* RS Hc, const double* RS dinv,
+                                         const int wid, const int lane) {
+  constexpr int HCS = DENSE_HCS;
+#pragma unroll kSchurUnroll
+  for (int k = 0; k < NY; ++k) {
+    const double dk = dinv[k];
+    const double* hr = Hc + k * HCS;
+    double av[D3_RCH], bv[D3_CPW];
+#pragma unroll
+    for (int b = 0; b < D3_RCH; ++b) av[b] = hr[min(lane + 32 * b, NRED)] * dk;
+#pragma unroll
+    for (int a = 0; a < D3_CPW; ++a) bv[a] = hr[min(wid + 16 * a, NRED)];
+#pragma unroll
+    for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+      for (int a = 0; a < D3_CPW; ++a) acc[b][a] = fma(av[b], bv[a], acc[b][a]);
+  }
+}
+
+// the register tile of the direct part (G_x + tol·I)ᵀ, built once per solve in the L2-resident block Gc
+__device__ __forceinline__ void d3_load_tile(double (&acc)[D3_RCH][D3_CPW], const double* Gc, const int wid, const int lane) {
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+    for (int a = 0; a < D3_CPW; ++a) {
+      const int r = lane + 32 * b, c = wid + 16 * a;
+      acc[b][a] = (r < NRED && c < NRED) ? __ldcg(Gc + c * D3_GLD + r) : 0.0;
+    }
+}
+
 extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const SolveParams p) {
   extern __shared__ double smem[];
   const int t = threadIdx.x;
@@ -1109,6 +1338,21 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
       __stcg(Gc + D_CPOS[d] * D3_GLD + D_ROW[d], a0);
     }
     __syncthreads();
+    // is G_x + tol·I symmetric (to 1e-14 relative, far inside the factorisation's own backward error)?  NaN ⇒ no.
+    bool use_sym = false;
+#if D3_SYM
+    {
+      bool symok = true;
+      for (int idx = t; idx < NRED * NRED; idx += DT) {
+        const int r = idx / NRED, c = idx - r * NRED;
+        if (r > c) {
+          const double lo = __ldcg(Gc + c * D3_GLD + r), up = __ldcg(Gc + r * D3_GLD + c);
+          symok = symok && (fabs(lo - up) <= 1e-14 * (fabs(lo) + fabs(up)));
+        }
+      }
+      use_sym = __syncthreads_and(symok);
+    }
+#endif
     bool parked = false;
     while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
       if (p.pass == 0 && p.step_budget > 0 && steps >= p.step_budget) {
@@ -1121,13 +1365,7 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
         for (int c = t; c < NRED; c += DT) xt[c] = x[PERM[c]];
         // ---- tile of the direct part G_x + tol·I ------------------------------------------------------------------
         double acc[D3_RCH][D3_CPW];
-#pragma unroll
-        for (int b = 0; b < D3_RCH; ++b)
-#pragma unroll
-          for (int a = 0; a < D3_CPW; ++a) {
-            const int r = lane + 32 * b, c = wid + 16 * a;
-            acc[b][a] = (r < NRED && c < NRED) ? __ldcg(Gc + c * D3_GLD + r) : 0.0;
-          }
+        d3_load_tile(acc, Gc, wid, lane);
         __syncthreads();
         // ---- F (:79) from the affine structure: H = H(0) + H_x x,  G = G(0) + G_x x + G_y y,  G_y = −H_xᵀ ----------
         {
@@ -1192,34 +1430,40 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
           if (NY & 1) a0 = fma(Hc[(NY - 1) * HCS + t], w[NY - 1], a0);
           sol[t] = a0 + a1;
         }
-        // ---- Schur part: C −= G_y D⁻¹ H_x = + H_xᵀ D⁻¹ H_x, accumulated on the register tiles ----------------------
-#pragma unroll kSchurUnroll
-        for (int k = 0; k < NY; ++k) {
-          const double dk = dinv[k];
-          const double* hr = Hc + k * HCS;
-          double av[D3_RCH], bv[D3_CPW];
-#pragma unroll
-          for (int b = 0; b < D3_RCH; ++b) av[b] = hr[min(lane + 32 * b, NRED)] * dk;
-#pragma unroll
-          for (int a = 0; a < D3_CPW; ++a) bv[a] = hr[min(wid + 16 * a, NRED)];
-#pragma unroll
-          for (int b = 0; b < D3_RCH; ++b)
-#pragma unroll
-            for (int a = 0; a < D3_CPW; ++a) acc[b][a] = fma(av[b], bv[a], acc[b][a]);
-        }
-        __syncthreads();
-        if (wid == (NRED & 15)) {
-#pragma unroll
-          for (int b = 0; b < D3_RCH; ++b) acc[b][NRED >> 4] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
-        }
-        // ---- LU with partial pivoting in registers; forward substitution rides in column NRED -----------------------
+        // ---- Schur part: C −= G_y D⁻¹ H_x = + H_xᵀ D⁻¹ H_x, accumulated on the register tiles; factorisation with the
+        //      forward substitution riding in column NRED -------------------------------------------------------------
         bool failed = false;
+        do {
+#if D3_SYM
+        if (use_sym) {
+          double T[D3_RCH][D3_RCH][2], rv[D3_RCH];
+          const bool lastrow = lane + 32 * (D3_RCH - 1) < NRED;
+          d3p_assemble(T, Gc, Hc, dinv, wid, lane);
+          __syncthreads();   // sol (the right-hand side) is complete, the staging use of UT is over
+#pragma unroll
+          for (int b = 0; b < D3_RCH; ++b) rv[b] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
+#if D3_SYM_LOOKAHEAD
+          if (wid == 0) d3p_panel<0>(T, lane, 0, 0, UT, rd, lastrow);
+#endif
+          if (!d3p_blocks<0>(T, rv, wid, lane, rd, UT, lastrow)) break;
+          use_sym = false;   // a pivot was not positive: pivoted LU from here on
+          __syncthreads();
+          d3_load_tile(acc, Gc, wid, lane);
+        }
+#endif
         {
+          d3_schur(acc, Hc, dinv, wid, lane);
+          __syncthreads();
+          if (wid == (NRED & 15)) {
+#pragma unroll
+            for (int b = 0; b < D3_RCH; ++b) acc[b][NRED >> 4] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
+          }
 #if D3_LOOKAHEAD
           if (wid == 0) d3_search<0>(acc, lane, 0, mbuf, sh_pr, rd);
 #endif
           failed = d3_lu_blocks<0>(acc, wid, lane, mbuf, sh_pr, rd, UT);
         }
+        } while (false);
         __syncthreads();   // UT, rd complete (failed is CTA-uniform: every thread read the same key and pivot)
         double a_s = 1.0, a_y = 1.0;
         if (!failed) {
