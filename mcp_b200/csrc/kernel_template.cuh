@@ -1070,21 +1070,16 @@ __device__ __forceinline__ void d3p_panel(double (&T)[D3_RCH][D3_RCH][2], const 
                                           double* UT, double* rd, const bool lastrow) {
   constexpr int UTLD = DENSE_UTLD;
   const bool two = j0 + 1 < NRED;
-  double* q = UT + lane * UTLD + j0;
-#pragma unroll
-  for (int b = A; b < D3_RCH; ++b)
-    if (b < D3_RCH - 1 || lastrow) q[32 * b * UTLD] = T[b][A][0];
   const double d0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo);
   const double u0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo + 1);   // U[j0][j0+1]
   const double rp0 = d3_rcp(d0);
 #pragma unroll
   for (int b = A; b < D3_RCH; ++b) T[b][A][1] = fma(-(T[b][A][0] * rp0), u0, T[b][A][1]);
   const double d1 = __shfl_sync(FULLMASK, T[A][A][1], 2 * wo + 1);
-  if (two) {
+  double2* q = reinterpret_cast<double2*>(UT + lane * UTLD + j0);   // (even row stride, even j0: 16-byte aligned)
 #pragma unroll
-    for (int b = A; b < D3_RCH; ++b)
-      if (b < D3_RCH - 1 || lastrow) q[32 * b * UTLD + 1] = T[b][A][1];
-  }
+  for (int b = A; b < D3_RCH; ++b)
+    if (b < D3_RCH - 1 || lastrow) q[16 * b * UTLD] = make_double2(T[b][A][0], T[b][A][1]);   // (cell j0+1 = NRED is unused)
   const double rp1 = d3_rcp(d1);
   if (lane == 0) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -1101,9 +1096,9 @@ __device__ __forceinline__ void d3p_update(double (&T)[D3_RCH][D3_RCH][2], const
   const int c0 = 32 * AC + 2 * wid;
   // (only the last column block can run past the matrix: padding columns read the right-hand-side row, finite or
   // not — their tile entries are never read)
-  const double* q0 = UT + (AC == D3_RCH - 1 ? min(c0, NRED) : c0) * UTLD + j0;
-  const double* q1 = UT + (AC == D3_RCH - 1 ? min(c0 + 1, NRED) : c0 + 1) * UTLD + j0;
-  const double u00 = q0[0], u01 = q0[1], u10 = q1[0], u11 = q1[1];
+  const double2 v0 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0, NRED) : c0) * UTLD + j0);
+  const double2 v1 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0 + 1, NRED) : c0 + 1) * UTLD + j0);
+  const double u00 = v0.x, u01 = v0.y, u10 = v1.x, u11 = v1.y;
 #pragma unroll
   for (int b = (AC > AB ? AC : AB); b < D3_RCH; ++b) {
     T[b][AC][0] = fma(m1[b], u01, fma(m0[b], u00, T[b][AC][0]));
@@ -1138,9 +1133,9 @@ __device__ __forceinline__ bool d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], doubl
       double m0[D3_RCH], m1[D3_RCH];
 #pragma unroll
       for (int b = A; b < D3_RCH; ++b) {
-        const double* q = (b == D3_RCH - 1 ? mql : mq + 32 * b * UTLD) + j0;
-        m0[b] = -(q[0] * rp0);
-        m1[b] = two ? -(q[1] * rp1) : 0.0;
+        const double2 v = *reinterpret_cast<const double2*>((b == D3_RCH - 1 ? mql : mq + 32 * b * UTLD) + j0);
+        m0[b] = -(v.x * rp0);
+        m1[b] = two ? -(v.y * rp1) : 0.0;
       }
       int la = -1;   // column block already updated by the look-ahead
 #if D3_SYM_LOOKAHEAD
@@ -1223,6 +1218,48 @@ __device__ __forceinline__ void d3p_assemble(double (&T)[D3_RCH][D3_RCH][2], con
   }
 }
 
+// The same tile when H_x is sparse IN VALUE (the benchmark's A has 10 % non-zeros; the plan only knows that every
+// entry is a parameter): row i of C = (G_x + tol·I) + Σ_k (H_x[k,i]·D⁻¹_k)·H_x[k,:] only sums the constraints k with
+// H_x[k,i] ≠ 0 — listed once per solve (KLIST / kcnt) — in the same order, so the values are those of the dense
+// accumulation (the skipped terms are ±0).  Warp w builds rows i ≡ w (mod 16) in registers, lanes over the columns,
+// into S (the Uᵀ array, free at this point); the tiles are then read from S with 128-bit loads.
+__device__ __forceinline__ void d3p_assemble_sparse(double (&T)[D3_RCH][D3_RCH][2], const double* Gc, const double* RS Hc,
+                                                    const double* RS dinv, const unsigned char* RS KLIST, const int* RS kcnt,
+                                                    double* S, const int wid, const int lane) {
+  constexpr int HCS = DENSE_HCS, UTLD = DENSE_UTLD, KLS = DENSE_KLS;
+  int ji[D3_RCH];
+#pragma unroll
+  for (int q = 0; q < D3_RCH; ++q) ji[q] = min(lane + 32 * q, NRED);   // column NRED of the cached H_x stays 0
+  for (int i = wid; i < NRED; i += DT / 32) {
+    double sa[D3_RCH];
+#pragma unroll
+    for (int q = 0; q < D3_RCH; ++q) sa[q] = (lane + 32 * q < NRED) ? __ldcg(Gc + i * D3_GLD + lane + 32 * q) : 0.0;
+    const unsigned char* kl = KLIST + i * KLS;
+    const int n = kcnt[i];
+#pragma unroll 4
+    for (int e = 0; e < n; ++e) {
+      const int k = kl[e];
+      const double* hr = Hc + k * HCS;
+      const double av = hr[i] * dinv[k];
+#pragma unroll
+      for (int q = 0; q < D3_RCH; ++q) sa[q] = fma(av, hr[ji[q]], sa[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < D3_RCH; ++q)
+      if (lane + 32 * q < NRED) S[i * UTLD + lane + 32 * q] = sa[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < D3_RCH; ++b)
+#pragma unroll
+    for (int a = 0; a <= b; ++a) {
+      const int r = min(lane + 32 * b, NRED - 1), c = min(32 * a + 2 * wid, UTLD - 2);   // (padding: any finite cell)
+      const double2 v = *reinterpret_cast<const double2*>(S + r * UTLD + c);
+      T[b][a][0] = v.x;
+      T[b][a][1] = v.y;
+    }
+}
+
 // + H_xᵀ D⁻¹ H_x on the register tiles of the LU layout, one rank-1 update per constraint from the cached H_x (4
 // conflict-free + 7 broadcast shared loads per 28 DFMAs)
 __device__ __forceinline__ void d3_schur(double (&acc)[D3_RCH][D3_CPW], const double* RS Hc, const double* RS dinv,
@@ -1274,11 +1311,14 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
   double* gh0 = smem + DENSE_OFF_G0;     // G(0;θ), H(0;θ)
   double* UT = smem + DENSE_OFF_UT;      // Uᵀ in pivot order: UT[c·UTLD + step]; row NRED = forward-substituted rhs
   double* mbuf = smem + DENSE_OFF_MBUF;  // 2 × 128 multipliers of the current column (double-buffered by parity)
+  unsigned char* KLIST = reinterpret_cast<unsigned char*>(smem + DENSE_OFF_KL);   // non-zeros of H_x by column
+  int* kcnt = reinterpret_cast<int*>(smem + DENSE_OFF_KCNT);
   double* Gc = p.scratch + (size_t)blockIdx.x * SOLVE_SCRATCH;  // (G_x + tol·I)ᵀ, NRED columns × D3_GLD
   constexpr int HCS = DENSE_HCS;
   constexpr int UTLD = DENSE_UTLD;
   __shared__ unsigned long long sh_q;
   __shared__ int sh_pr[2];
+  __shared__ int sh_nnz;
 #if THETA_IN_SMEM
   double* th = smem + DENSE_OFF_TH;
 #else
@@ -1289,7 +1329,10 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
 
   for (;;) {
     __syncthreads();
-    if (t == 0) sh_q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+    if (t == 0) {
+      sh_q = atomicAdd(p.counters + (p.pass ? 4 : 0), 1ULL);
+      sh_nnz = 0;
+    }
     __syncthreads();
     unsigned long long inst = sh_q;
     if (p.pass) {
@@ -1352,6 +1395,31 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
       }
       use_sym = __syncthreads_and(symok);
     }
+    // the non-zeros of H_x by column, for the sparse form of the Schur product (d3p_assemble_sparse)
+    bool sparse_hx = false;
+#ifndef D3_SPARSE_SCHUR
+#define D3_SPARSE_SCHUR 1
+#endif
+#if D3_SPARSE_SCHUR
+    if (use_sym) {
+      for (int i = wid; i < NRED; i += DT / 32) {
+        int base = 0;
+        for (int kb = 0; kb < NY; kb += 32) {
+          const int k = kb + lane;
+          const bool nz = k < NY && Hc[k * HCS + i] != 0.0;   // (a NaN counts as a non-zero)
+          const unsigned bal = __ballot_sync(FULLMASK, nz);
+          if (nz) KLIST[i * DENSE_KLS + base + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)k;
+          base += __popc(bal);
+        }
+        if (lane == 0) {
+          kcnt[i] = base;
+          atomicAdd(&sh_nnz, base);
+        }
+      }
+      __syncthreads();
+      sparse_hx = 3 * sh_nnz <= NY * NRED;   // denser than a third: the dense accumulation is the faster one
+    }
+#endif
 #endif
     bool parked = false;
     while (kkt > tol && eps > tol && outer < p.max_outer) {  // :71
@@ -1438,8 +1506,13 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
         if (use_sym) {
           double T[D3_RCH][D3_RCH][2], rv[D3_RCH];
           const bool lastrow = lane + 32 * (D3_RCH - 1) < NRED;
-          d3p_assemble(T, Gc, Hc, dinv, wid, lane);
-          __syncthreads();   // sol (the right-hand side) is complete, the staging use of UT is over
+          if (sparse_hx) {
+            __syncthreads();   // the staging use of UT is over, D⁻¹ is complete
+            d3p_assemble_sparse(T, Gc, Hc, dinv, KLIST, kcnt, UT, wid, lane);
+          } else {
+            d3p_assemble(T, Gc, Hc, dinv, wid, lane);
+          }
+          __syncthreads();   // sol (the right-hand side) is complete; every tile is loaded before Uᵀ is written
 #pragma unroll
           for (int b = 0; b < D3_RCH; ++b) rv[b] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
 #if D3_SYM_LOOKAHEAD
@@ -1472,19 +1545,36 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
             double rhs[D3_RCH];
 #pragma unroll
             for (int b = 0; b < D3_RCH; ++b) rhs[b] = (lane + 32 * b < NRED) ? UT[NRED * UTLD + lane + 32 * b] : 0.0;
+            // (two columns per trip — one round of shuffles, the 2×2 block solved in registers; same operations in the
+            // same order as column by column)
 #pragma unroll
             for (int bj = D3_RCH - 1; bj >= 0; --bj) {
-#pragma unroll 4
-              for (int lj = 31; lj >= 0; --lj) {
-                const int j = bj * 32 + lj;
-                if (j < NRED) {
-                  const double xj = __shfl_sync(FULLMASK, rhs[bj], lj) * rd[j];
-                  if (lane == lj) sol[j] = xj;
-                  const double* uc = UT + j * UTLD;
+#pragma unroll 2
+              for (int lp = 15; lp >= 0; --lp) {
+                const int j0 = bj * 32 + 2 * lp, j1 = j0 + 1;
+                if (j0 >= NRED) continue;
+                const double* uc0 = UT + j0 * UTLD;
+                const double r0 = __shfl_sync(FULLMASK, rhs[bj], 2 * lp);
+                if (j1 < NRED) {
+                  const double* uc1 = UT + j1 * UTLD;
+                  const double x1 = __shfl_sync(FULLMASK, rhs[bj], 2 * lp + 1) * rd[j1];
+                  const double x0 = fma(-uc1[j0], x1, r0) * rd[j0];
+                  if (lane == 0) {
+                    sol[j0] = x0;
+                    sol[j1] = x1;
+                  }
 #pragma unroll
                   for (int b = 0; b <= bj; ++b) {
                     const int i = lane + 32 * b;
-                    if (i < j) rhs[b] = fma(-uc[i], xj, rhs[b]);
+                    if (i < j0) rhs[b] = fma(-uc0[i], x0, fma(-uc1[i], x1, rhs[b]));
+                  }
+                } else {
+                  const double x0 = r0 * rd[j0];
+                  if (lane == 0) sol[j0] = x0;
+#pragma unroll
+                  for (int b = 0; b <= bj; ++b) {
+                    const int i = lane + 32 * b;
+                    if (i < j0) rhs[b] = fma(-uc0[i], x0, rhs[b]);
                   }
                 }
               }

@@ -1383,7 +1383,11 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     bool want_v3 = P.dense_kernel == 2 && N + 1 <= 112 && ny <= 128;
     if (const char* e = getenv("MCPB200_DENSE_KERNEL")) want_v3 = want_v3 && atoi(e) >= 3;
     if (want_v3) {
-      const int64_t hcs = (N + 1) | 1, utld = N | 1;
+      // Uᵀ row stride ≡ 2 (mod 4) and > N: the symmetric path reads and writes column PAIRS (two adjacent steps) as
+      // 128-bit accesses, conflict-free across the lanes of a quarter-warp, broadcast for the pivot-row entries
+      int64_t utld = N + 1;
+      while (utld % 4 != 2) ++utld;
+      const int64_t hcs = (N + 1) | 1, kls = (ny + 7) & ~int64_t(7);
       const int64_t off_v2 = off;
       off = 0;
       place("DENSE_OFF_X", nx);
@@ -1402,12 +1406,14 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       place("DENSE_OFF_G0", nx + ny);
       place("DENSE_OFF_UT", std::max<int64_t>((int64_t)(N + 1) * utld, 16 * 128));
       place("DENSE_OFF_MBUF", 2 * 128);
+      place("DENSE_OFF_KL", (int64_t)N * kls / 8);    // per column of H_x: the constraints with a non-zero entry (bytes)
+      place("DENSE_OFF_KCNT", (N + 1) / 2);           // … and how many (ints)
       if (off * 8 <= kSmemBudget) {
         P.dense_kernel = 3;
         P.dense_threads = 512;
         P.smem_solve = off * 8;
         P.dense_ctas_per_sm = 1;
-        lay << "#define DENSE_UTLD " << utld << "\n";
+        lay << "#define DENSE_UTLD " << utld << "\n#define DENSE_KLS " << kls << "\n";
       } else {
         off = off_v2;
       }

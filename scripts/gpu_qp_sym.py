@@ -51,6 +51,9 @@ out["parity"].append(parity(qp, Θa, "asymmetric M (LU fallback by the symmetry 
 for i in (5, 40):
     Θi[i + 100 * i] -= 30.0
 out["parity"].append(parity(qp, Θi, "indefinite symmetric M (LU fallback on a non-positive pivot)"))
+# dense A (70 % non-zeros): the dense form of the Schur accumulation
+Θd = problems.random_qp_thetas(16, seed=3, sparsity_rate=0.3)
+out["parity"].append(parity(qp, Θd, "dense A and M (dense Schur accumulation)"))
 h = _handle(qp)
 info = h.info()
 for B in BATCHES:
