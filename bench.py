@@ -258,7 +258,7 @@ def other_workloads(local: int, fp64_peak: float, hbm_gbs: float, reps: int = 3)
     out["cfg1_readme_qp_tol1e-6"], _, _ = solve_entry(mcp, Θ, 1e-6, e2e=False)
     # cfg2 — random convex QP 100×100: cold, then the θ sweep (ϕ ← ϕ + 0.01·N(0,1)) warm-started from the cold solution
     mcp = problems.random_qp(100, 100)
-    Bq = 1 << 13
+    Bq = 1 << 14
     Θ = problems.random_qp_thetas(Bq, seed=1)
     cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1")
     out["cfg2_random_qp_cold"] = cold

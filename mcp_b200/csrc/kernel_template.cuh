@@ -1048,10 +1048,42 @@ __device__ __forceinline__ bool d3_lu_blocks(double (&acc)[D3_RCH][D3_CPW], cons
 #ifndef D3_SYM
 #define D3_SYM 1
 #endif
-#ifndef D3_SYM_LOOKAHEAD
-#define D3_SYM_LOOKAHEAD 1
-#endif
 #define D3P_RW 15   // warp that carries the right-hand side
+
+// One mbarrier per panel instead of a CTA-wide barrier per panel (D3_SYM_MBAR): the owner arrives once its panel is
+// in shared memory, everybody else waits for THAT — not for the other fourteen warps — so the warps drift apart, their
+// bursts of shared-memory loads no longer collide right after a barrier, and a warp that is late (the one carrying
+// the right-hand side, the next owner) delays nobody who does not need its data.  Every cell of Uᵀ / rd is written
+// once per factorisation, so there is nothing to protect against overwriting.  Each barrier completes once per
+// factorisation: the waiters' phase parity is the parity of the factorisation count since the (per-solve) init.
+#ifndef D3_SYM_MBAR
+#define D3_SYM_MBAR 1
+#endif
+#define D3P_NP ((NRED + 1) / 2)
+__device__ __forceinline__ void d3_mbar_init(unsigned long long* bar, const unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void d3_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void d3_mbar_wait(unsigned long long* bar, const unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done) {   // a logic error must not hang the device: give up (launch failure) after ~1 s
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 2000000000LL) __trap();
+    }
+  } while (!done);
+}
 
 __device__ __forceinline__ double d3_rcp(const double d) {
   double rp;
@@ -1062,58 +1094,103 @@ __device__ __forceinline__ double d3_rcp(const double d) {
   return fma(rp, er, rp);
 }
 
-// Factorise the panel (columns j0, j0+1) held by the calling warp `wo` in column block A, whose entries are up to
+// The 2×2 diagonal block of the calling warp's NEXT panel, kept redundantly by all its lanes: dg = (a00, a10, a11).
+// It receives the same two FMAs per panel as the tile entries it mirrors (lanes 2w, 2w+1 of chunk AD), from the
+// same operands — the pivot-row entries of the warp's own columns, which are also the multipliers of those two rows —
+// so it is bit-identical to them, and the panel's factorisation needs no shuffle: the owner's critical path is
+// wait → loads → arithmetic → stores → arrive.
+__device__ __forceinline__ void d3p_diag_update(double (&dg)[3], const double2 v0, const double2 v1, const double rp0,
+                                                const double rp1, const bool two) {
+  const double ma0 = -(v0.x * rp0), mb0 = -(v1.x * rp0);          // multipliers of rows c0, c0+1 for step j0
+  const double ma1 = two ? -(v0.y * rp1) : 0.0, mb1 = two ? -(v1.y * rp1) : 0.0;   // … for step j0+1
+  dg[0] = fma(ma1, v0.y, fma(ma0, v0.x, dg[0]));
+  dg[1] = fma(mb1, v0.y, fma(mb0, v0.x, dg[1]));
+  dg[2] = fma(mb1, v1.y, fma(mb0, v1.x, dg[2]));
+}
+
+template <int AD>
+__device__ __forceinline__ void d3p_diag_seed(double (&dg)[3], const double (&T)[D3_RCH][D3_RCH][2], const int wid) {
+  if constexpr (AD < D3_RCH) {
+    dg[0] = __shfl_sync(FULLMASK, T[AD][AD][0], 2 * wid);
+    dg[1] = __shfl_sync(FULLMASK, T[AD][AD][0], 2 * wid + 1);
+    dg[2] = __shfl_sync(FULLMASK, T[AD][AD][1], 2 * wid + 1);
+  }
+}
+
+// Factorise the panel (columns j0, j0+1) held by the calling warp in column block A, whose entries (and dg) are up to
 // date with every earlier panel, and publish it: UT[r·UTLD + j] = entry (r, j) for the rows of chunks ≥ A (rows
 // above the diagonal land in cells nothing reads), rd[j] = 1/d_j — NaN when d_j is not positive and finite.
 template <int A>
-__device__ __forceinline__ void d3p_panel(double (&T)[D3_RCH][D3_RCH][2], const int lane, const int wo, const int j0,
-                                          double* UT, double* rd, const bool lastrow) {
+__device__ __forceinline__ void d3p_panel(double (&T)[D3_RCH][D3_RCH][2], const double (&dg)[3], const int lane,
+                                          const int j0, double* UT, double* rd, const bool lastrow,
+                                          unsigned long long* bars) {
   constexpr int UTLD = DENSE_UTLD;
   const bool two = j0 + 1 < NRED;
-  const double d0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo);
-  const double u0 = __shfl_sync(FULLMASK, T[A][A][0], 2 * wo + 1);   // U[j0][j0+1]
+  const double d0 = dg[0], u0 = dg[1];   // u0 = U[j0][j0+1]
   const double rp0 = d3_rcp(d0);
-#pragma unroll
-  for (int b = A; b < D3_RCH; ++b) T[b][A][1] = fma(-(T[b][A][0] * rp0), u0, T[b][A][1]);
-  const double d1 = __shfl_sync(FULLMASK, T[A][A][1], 2 * wo + 1);
+  const double d1 = fma(-(u0 * rp0), u0, dg[2]);
+  const double rp1 = d3_rcp(d1);
   double2* q = reinterpret_cast<double2*>(UT + lane * UTLD + j0);   // (even row stride, even j0: 16-byte aligned)
 #pragma unroll
-  for (int b = A; b < D3_RCH; ++b)
+  for (int b = A; b < D3_RCH; ++b) {
+    T[b][A][1] = fma(-(T[b][A][0] * rp0), u0, T[b][A][1]);
     if (b < D3_RCH - 1 || lastrow) q[16 * b * UTLD] = make_double2(T[b][A][0], T[b][A][1]);   // (cell j0+1 = NRED is unused)
-  const double rp1 = d3_rcp(d1);
+  }
   if (lane == 0) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     rd[j0] = (d0 > 0.0 && d0 <= DBL_MAX_ && rp0 == rp0) ? rp0 : qnan;
     if (two) rd[j0 + 1] = (d1 > 0.0 && d1 <= DBL_MAX_ && rp1 == rp1) ? rp1 : qnan;
   }
+#if D3_SYM_MBAR
+  __syncwarp();   // every lane's cells before the one arrival
+  if (lane == 0) d3_mbar_arrive(bars + (j0 >> 1));
+#endif
 }
 
-// rank-2 update of the calling thread's tile block (b ≥ AC, column block AC) with panel (j0, j0+1)
-template <int AC, int AB>
-__device__ __forceinline__ void d3p_update(double (&T)[D3_RCH][D3_RCH][2], const double (&m0)[D3_RCH],
-                                           const double (&m1)[D3_RCH], const double* RS UT, const int wid, const int j0) {
+// the pivot-row entries of the calling warp's two columns of block AC for panel (j0, j0+1)
+template <int AC>
+__device__ __forceinline__ void d3p_load_u(double2& v0, double2& v1, const double* RS UT, const int wid, const int j0) {
   constexpr int UTLD = DENSE_UTLD;
   const int c0 = 32 * AC + 2 * wid;
   // (only the last column block can run past the matrix: padding columns read the right-hand-side row, finite or
   // not — their tile entries are never read)
-  const double2 v0 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0, NRED) : c0) * UTLD + j0);
-  const double2 v1 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0 + 1, NRED) : c0 + 1) * UTLD + j0);
-  const double u00 = v0.x, u01 = v0.y, u10 = v1.x, u11 = v1.y;
+  v0 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0, NRED) : c0) * UTLD + j0);
+  v1 = *reinterpret_cast<const double2*>(UT + (AC == D3_RCH - 1 ? min(c0 + 1, NRED) : c0 + 1) * UTLD + j0);
+}
+
+// rank-2 update of the calling thread's tile block (b ≥ AC, column block AC) with panel (j0, j0+1)
+template <int AC>
+__device__ __forceinline__ void d3p_apply(double (&T)[D3_RCH][D3_RCH][2], const double (&m0)[D3_RCH],
+                                          const double (&m1)[D3_RCH], const double2 v0, const double2 v1) {
 #pragma unroll
-  for (int b = (AC > AB ? AC : AB); b < D3_RCH; ++b) {
-    T[b][AC][0] = fma(m1[b], u01, fma(m0[b], u00, T[b][AC][0]));
-    T[b][AC][1] = fma(m1[b], u11, fma(m0[b], u10, T[b][AC][1]));
+  for (int b = AC; b < D3_RCH; ++b) {
+    T[b][AC][0] = fma(m1[b], v0.y, fma(m0[b], v0.x, T[b][AC][0]));
+    T[b][AC][1] = fma(m1[b], v1.y, fma(m0[b], v1.x, T[b][AC][1]));
   }
 }
 
-// The panels of column block A (columns 32·A … 32·A+31, owner warps 0 … 15 in turn); returns true when a pivot was not
-// positive (the caller falls back to the pivoted LU).
+template <int AC>
+__device__ __forceinline__ void d3p_update(double (&T)[D3_RCH][D3_RCH][2], const double (&m0)[D3_RCH],
+                                           const double (&m1)[D3_RCH], const double* RS UT, const int wid, const int j0) {
+  if constexpr (AC < D3_RCH) {
+    double2 v0, v1;
+    d3p_load_u<AC>(v0, v1, UT, wid, j0);
+    d3p_apply<AC>(T, m0, m1, v0, v1);
+  }
+}
+
+// The panels of column block A (columns 32·A … 32·A+31, owner warps 0 … 15 in turn); returns −1, or the index of the
+// panel whose pivot was not positive (the caller falls back to the pivoted LU; nothing beyond that panel has been
+// published or signalled, because the look-ahead comes after the test).  On entry the panel (32·A, 32·A+1) has
+// been published by warp 0 and dg mirrors the diagonal block of the calling warp's next panel (block A for warps
+// whose turn is still to come, block A+1 for warp 0).
 template <int A>
-__device__ __forceinline__ bool d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], double (&rv)[D3_RCH], const int wid,
-                                           const int lane, double* rd, double* UT, const bool lastrow) {
+__device__ __forceinline__ int d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], double (&rv)[D3_RCH], double (&dg)[3],
+                                          const int wid, const int lane, double* rd, double* UT, const bool lastrow,
+                                          unsigned long long* bars, const unsigned parity) {
   constexpr int UTLD = DENSE_UTLD;
   if constexpr (A >= D3_RCH) {
-    return false;
+    return -1;
   } else {
     // my rows' cells of Uᵀ (rows of chunks ≥ A are still live; padding rows read the right-hand-side row)
     const double* mq = UT + lane * UTLD;
@@ -1123,42 +1200,54 @@ __device__ __forceinline__ bool d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], doubl
       const int j0 = 32 * A + 2 * wo;
       if (j0 >= NRED) break;
       const bool two = j0 + 1 < NRED;
-#if !D3_SYM_LOOKAHEAD
-      if (wid == wo) d3p_panel<A>(T, lane, wo, j0, UT, rd, lastrow);
-#endif
+      const bool mine_ahead = wid > wo;   // my panel of block A is still to come: dg mirrors block A, else block A+1
+#if D3_SYM_MBAR
+      d3_mbar_wait(bars + (j0 >> 1), parity);
+#else
       __syncthreads();
+#endif
+      // every load of the step up front (they do not depend on the pivot test)
       const double rp0 = rd[j0];
       const double rp1 = two ? rd[j0 + 1] : 0.0;
-      if (!(rp0 == rp0) || !(rp1 == rp1)) return true;
+      double2 mv[D3_RCH], vd0, vd1;
+#pragma unroll
+      for (int b = A; b < D3_RCH; ++b)
+        mv[b] = *reinterpret_cast<const double2*>((b == D3_RCH - 1 ? mql : mq + 32 * b * UTLD) + j0);
+      if (mine_ahead) {
+        d3p_load_u<A>(vd0, vd1, UT, wid, j0);
+      } else if constexpr (A + 1 < D3_RCH) {
+        d3p_load_u<A + 1>(vd0, vd1, UT, wid, j0);
+      }
+      if (!(rp0 == rp0) || !(rp1 == rp1)) return j0 >> 1;
+      if (mine_ahead || A + 1 < D3_RCH) d3p_diag_update(dg, vd0, vd1, rp0, rp1, two);
       double m0[D3_RCH], m1[D3_RCH];
 #pragma unroll
       for (int b = A; b < D3_RCH; ++b) {
-        const double2 v = *reinterpret_cast<const double2*>((b == D3_RCH - 1 ? mql : mq + 32 * b * UTLD) + j0);
-        m0[b] = -(v.x * rp0);
-        m1[b] = two ? -(v.y * rp1) : 0.0;
+        m0[b] = -(mv[b].x * rp0);
+        m1[b] = two ? -(mv[b].y * rp1) : 0.0;
       }
-      int la = -1;   // column block already updated by the look-ahead
-#if D3_SYM_LOOKAHEAD
-      if (j0 + 2 < NRED) {
-        if (wo < 15) {
-          if (wid == wo + 1) {
-            d3p_update<A, A>(T, m0, m1, UT, wid, j0);
-            d3p_panel<A>(T, lane, wid, j0 + 2, UT, rd, lastrow);
-            la = A;
-          }
-        } else if constexpr (A + 1 < D3_RCH) {
-          if (wid == 0) {
-            d3p_update<A + 1, A>(T, m0, m1, UT, wid, j0);
-            d3p_panel<A + 1>(T, lane, 0, j0 + 2, UT, rd, lastrow);
-            la = A + 1;
-          }
+      // look-ahead: the owner of the next panel brings its block up to date, factorises and publishes it first
+      bool reseed = false;
+      if (mine_ahead) {
+        d3p_apply<A>(T, m0, m1, vd0, vd1);
+        if (wid == wo + 1 && j0 + 2 < NRED) {
+          d3p_panel<A>(T, dg, lane, j0 + 2, UT, rd, lastrow, bars);
+          reseed = true;
+        }
+      } else if constexpr (A + 1 < D3_RCH) {
+        d3p_apply<A + 1>(T, m0, m1, vd0, vd1);
+        if (wo == 15 && wid == 0 && j0 + 2 < NRED) {
+          d3p_panel<A + 1>(T, dg, lane, j0 + 2, UT, rd, lastrow, bars);
+          reseed = true;
         }
       }
-#endif
-      if (wid > wo && la != A) d3p_update<A, A>(T, m0, m1, UT, wid, j0);
-      if constexpr (A + 1 < D3_RCH) { if (la != A + 1) d3p_update<A + 1, A>(T, m0, m1, UT, wid, j0); }
-      if constexpr (A + 2 < D3_RCH) d3p_update<A + 2, A>(T, m0, m1, UT, wid, j0);
-      if constexpr (A + 3 < D3_RCH) d3p_update<A + 3, A>(T, m0, m1, UT, wid, j0);
+      if (mine_ahead) d3p_update<A + 1>(T, m0, m1, UT, wid, j0);
+      d3p_update<A + 2>(T, m0, m1, UT, wid, j0);
+      d3p_update<A + 3>(T, m0, m1, UT, wid, j0);
+      if (reseed) {   // my next panel is one column block further on
+        if (wo == 15) d3p_diag_seed<A + 2>(dg, T, wid);
+        else d3p_diag_seed<A + 1>(dg, T, wid);
+      }
       if (wid == D3P_RW) {   // forward substitution of the right-hand side (rows j0, j0+1 are in chunk A, lanes 2wo, 2wo+1)
         const double r0 = __shfl_sync(FULLMASK, rv[A], 2 * wo);
         if (lane == 0) UT[NRED * UTLD + j0] = r0;
@@ -1172,7 +1261,7 @@ __device__ __forceinline__ bool d3p_blocks(double (&T)[D3_RCH][D3_RCH][2], doubl
         }
       }
     }
-    return d3p_blocks<A + 1>(T, rv, wid, lane, rd, UT, lastrow);
+    return d3p_blocks<A + 1>(T, rv, dg, wid, lane, rd, UT, lastrow, bars, parity);
   }
 }
 
@@ -1319,6 +1408,9 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
   __shared__ unsigned long long sh_q;
   __shared__ int sh_pr[2];
   __shared__ int sh_nnz;
+#if D3_SYM
+  __shared__ unsigned long long d3_bars[D3P_NP];
+#endif
 #if THETA_IN_SMEM
   double* th = smem + DENSE_OFF_TH;
 #else
@@ -1326,6 +1418,12 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
 #endif
   const double tol = p.tol;
   const unsigned long long n_deferred = p.pass ? p.counters[3] : 0ULL;
+#if D3_SYM
+  unsigned nfact = 0;   // symmetric factorisations of this CTA (phase parity of the panel barriers)
+#if D3_SYM_MBAR
+  if (t < D3P_NP) d3_mbar_init(d3_bars + t, 1);   // one arrival (the panel's owner) completes a phase
+#endif
+#endif
 
   for (;;) {
     __syncthreads();
@@ -1515,12 +1613,21 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
           __syncthreads();   // sol (the right-hand side) is complete; every tile is loaded before Uᵀ is written
 #pragma unroll
           for (int b = 0; b < D3_RCH; ++b) rv[b] = (lane + 32 * b < NRED) ? sol[lane + 32 * b] : 0.0;
-#if D3_SYM_LOOKAHEAD
-          if (wid == 0) d3p_panel<0>(T, lane, 0, 0, UT, rd, lastrow);
-#endif
-          if (!d3p_blocks<0>(T, rv, wid, lane, rd, UT, lastrow)) break;
+          double dg[3];
+          d3p_diag_seed<0>(dg, T, wid);
+          if (wid == 0) {
+            d3p_panel<0>(T, dg, lane, 0, UT, rd, lastrow, d3_bars);
+            d3p_diag_seed<1>(dg, T, wid);
+          }
+          const unsigned par = nfact & 1u;
+          ++nfact;
+          const int pfail = d3p_blocks<0>(T, rv, dg, wid, lane, rd, UT, lastrow, d3_bars, par);
+          if (pfail < 0) break;
           use_sym = false;   // a pivot was not positive: pivoted LU from here on
           __syncthreads();
+#if D3_SYM_MBAR
+          if (t > pfail && t < D3P_NP) d3_mbar_arrive(d3_bars + t);   // every barrier completes once per factorisation
+#endif
           d3_load_tile(acc, Gc, wid, lane);
         }
 #endif

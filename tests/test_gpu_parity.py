@@ -321,6 +321,78 @@ def test_dense_kernel_shapes(n, m, threads):
         assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
 
 
+def _qp_vs_c_oracle(mcp, Θ):
+    """Every instance: same status as the C oracle; solved ones: Newton steps within ±1, x, y, s to the bar."""
+    from oracle import c_oracle as CO
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    ref = CO.solve_batch(mcp.ir, Θ, tol=1e-6)
+    np.testing.assert_array_equal(sol.status, ref.status)
+    ok = np.nonzero(sol.status == 0)[0]
+    assert np.all(np.abs(sol.newton_steps[ok] - ref.newton_steps[ok]) <= 1)
+    for b in ok:
+        assert rel_err(sol.x[:, b], ref.x[:, b]) <= RTOL and rel_err(sol.y[:, b], ref.y[:, b]) <= RTOL
+        assert rel_err(sol.s[:, b], ref.s[:, b]) <= RTOL
+    return sol, len(ok)
+
+
+def test_dense_symmetric_path_and_fallbacks():
+    """r2: when G_x (from θ) is symmetric the dense kernel factorises the condensed matrix by LDLᵀ without pivoting
+    (kernel_template.cuh, d3p_*), with the Schur product summed over the non-zeros of H_x only when H_x is sparse in
+    value.  The paths an instance can take — symmetric + sparse A (the benchmark's own generator), symmetric + dense A,
+    G_x not symmetric (symmetry check ⇒ pivoted LU), G_x symmetric but indefinite (non-positive pivot ⇒ pivoted LU
+    from that Newton step on) — all against the C oracle, which always runs the reference's pivoted sparse LU."""
+    mcp = problems.random_qp(100, 100)
+    Θ = problems.random_qp_thetas(48, seed=11)
+    _, n = _qp_vs_c_oracle(mcp, Θ)
+    assert n >= 44
+    _, n = _qp_vs_c_oracle(mcp, problems.random_qp_thetas(12, seed=3, sparsity_rate=0.3))   # dense A, dense M
+    assert n >= 10
+    Θa = Θ[:, :12].copy()
+    Θa[3 + 100 * 7] += 0.25      # vec(M) is column-major: M[r, c] = θ[r + 100 c]
+    Θa[50 + 100 * 2] -= 0.125
+    _, n = _qp_vs_c_oracle(mcp, Θa)
+    assert n >= 10
+    Θi = Θ[:, :12].copy()
+    for i in (5, 40):
+        Θi[i + 100 * i] -= 30.0  # two negative directions: LDLᵀ meets a negative pivot in the first Newton step
+    _, n = _qp_vs_c_oracle(mcp, Θi)
+    assert n >= 6
+
+
+def test_random_qp_batch_properties():
+    """cfg2 at a batch the oracle cannot follow (every CTA solves several instances back to back, both passes run):
+    size-independent checks on ALL instances with the QP's own data — stationarity M x − ϕ − Aᵀy, primal
+    feasibility A x − b = s ≥ 0, complementarity at the ϵ scale (the reference's `check_solution`-style assertions,
+    test/runtests.jl:30-38) — and a random sample against the C oracle."""
+    from oracle import c_oracle as CO
+    n = m = 100
+    mcp = problems.random_qp(n, m)
+    B = 1200
+    Θ = problems.random_qp_thetas(B, seed=21)
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    assert np.all((sol.status == 0) | (sol.status == 1))
+    ok = np.nonzero(sol.status == 0)[0]
+    assert len(ok) >= 0.98 * B
+    M = Θ[:n * n].reshape(n, n, B, order="F")
+    A = Θ[n * n:n * n + m * n].reshape(m, n, B, order="F")
+    b, ϕ = Θ[n * n + m * n:n * n + m * n + m], Θ[-n:]
+    G = np.einsum("ijb,jb->ib", M, sol.x) - ϕ - np.einsum("kib,kb->ib", A, sol.y)
+    H = np.einsum("kjb,jb->kb", A, sol.x) - b
+    scale = 1.0 + np.abs(sol.y[:, ok]).max(axis=0)
+    assert np.max(np.abs(G[:, ok]).max(axis=0) / scale) <= 1e-5
+    assert np.max(np.abs(H[:, ok] - sol.s[:, ok])) <= 1e-5
+    assert np.all(sol.y[:, ok] > 0) and np.all(sol.s[:, ok] > 0)
+    assert np.max(sol.s[:, ok] * sol.y[:, ok]) < 1e-2
+    assert np.all((sol.kkt_error[ok] <= 1e-6) | (sol.ϵ[ok] <= 1e-6))
+    idx = np.random.default_rng(1).choice(B, 24, replace=False)
+    ref = CO.solve_batch(mcp.ir, Θ[:, idx], tol=1e-6)
+    np.testing.assert_array_equal(sol.status[idx], ref.status)
+    for k, bb in enumerate(idx):
+        if ref.status[k] == 0:
+            assert abs(int(ref.newton_steps[k]) - int(sol.newton_steps[bb])) <= 1
+            assert rel_err(sol.x[:, bb], ref.x[:, k]) <= RTOL and rel_err(sol.y[:, bb], ref.y[:, k]) <= RTOL
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------------------
 def test_empty_and_single_batches(readme_mcp):
     empty = solve(InteriorPoint(), readme_mcp, np.zeros((2, 0)))
