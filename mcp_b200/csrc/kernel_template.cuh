@@ -1073,7 +1073,7 @@ __device__ __forceinline__ void d3_mbar_wait(unsigned long long* bar, const unsi
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, 2000;\n\t"   // (suspend-time hint, ns)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
@@ -1320,9 +1320,12 @@ __device__ __forceinline__ void d3p_assemble_sparse(double (&T)[D3_RCH][D3_RCH][
 #pragma unroll
   for (int q = 0; q < D3_RCH; ++q) ji[q] = min(lane + 32 * q, NRED);   // column NRED of the cached H_x stays 0
   for (int i = wid; i < NRED; i += DT / 32) {
+    // (only the column chunks up to the one holding the diagonal: the tiles read the lower triangle, whole diagonal
+    // blocks included)
     double sa[D3_RCH];
 #pragma unroll
-    for (int q = 0; q < D3_RCH; ++q) sa[q] = (lane + 32 * q < NRED) ? __ldcg(Gc + i * D3_GLD + lane + 32 * q) : 0.0;
+    for (int q = 0; q < D3_RCH; ++q)
+      sa[q] = (32 * q <= i && lane + 32 * q < NRED) ? __ldcg(Gc + i * D3_GLD + lane + 32 * q) : 0.0;
     const unsigned char* kl = KLIST + i * KLS;
     const int n = kcnt[i];
 #pragma unroll 4
@@ -1331,11 +1334,12 @@ __device__ __forceinline__ void d3p_assemble_sparse(double (&T)[D3_RCH][D3_RCH][
       const double* hr = Hc + k * HCS;
       const double av = hr[i] * dinv[k];
 #pragma unroll
-      for (int q = 0; q < D3_RCH; ++q) sa[q] = fma(av, hr[ji[q]], sa[q]);
+      for (int q = 0; q < D3_RCH; ++q)
+        if (32 * q <= i) sa[q] = fma(av, hr[ji[q]], sa[q]);
     }
 #pragma unroll
     for (int q = 0; q < D3_RCH; ++q)
-      if (lane + 32 * q < NRED) S[i * UTLD + lane + 32 * q] = sa[q];
+      if (32 * q <= i && lane + 32 * q < NRED) S[i * UTLD + lane + 32 * q] = sa[q];
   }
   __syncthreads();
 #pragma unroll
@@ -1653,37 +1657,56 @@ extern "C" __global__ void __launch_bounds__(DT, 1) mcp_solve_kernel(const Solve
 #pragma unroll
             for (int b = 0; b < D3_RCH; ++b) rhs[b] = (lane + 32 * b < NRED) ? UT[NRED * UTLD + lane + 32 * b] : 0.0;
             // (two columns per trip — one round of shuffles, the 2×2 block solved in registers; same operations in the
-            // same order as column by column)
+            // same order as column by column.  Everything a trip reads from shared memory — two reciprocal pivots, the
+            // cross entry, the two columns of Uᵀ — is loaded one trip ahead, so only shuffle → multiply → FMA is on the
+            // dependent chain)
+            constexpr int NPAIR = (NRED + 1) / 2;
+            double rdc0, rdc1, crc, uc0c[D3_RCH], uc1c[D3_RCH];
+            auto bs_load = [&](const int pp, double& r0_, double& r1_, double& cr_, double (&u0_)[D3_RCH], double (&u1_)[D3_RCH]) {
+              const int q0 = 2 * pp, q1 = min(q0 + 1, NRED - 1);   // (an odd NRED: the last pair's second column is a dummy)
+              r0_ = rd[q0];
+              r1_ = rd[q1];
+              cr_ = UT[q1 * UTLD + q0];
 #pragma unroll
-            for (int bj = D3_RCH - 1; bj >= 0; --bj) {
+              for (int b = 0; b < D3_RCH; ++b) {
+                u0_[b] = UT[q0 * UTLD + min(lane + 32 * b, NRED - 1)];
+                u1_[b] = UT[q1 * UTLD + min(lane + 32 * b, NRED - 1)];
+              }
+            };
+            bs_load(NPAIR - 1, rdc0, rdc1, crc, uc0c, uc1c);
 #pragma unroll 2
-              for (int lp = 15; lp >= 0; --lp) {
-                const int j0 = bj * 32 + 2 * lp, j1 = j0 + 1;
-                if (j0 >= NRED) continue;
-                const double* uc0 = UT + j0 * UTLD;
-                const double r0 = __shfl_sync(FULLMASK, rhs[bj], 2 * lp);
-                if (j1 < NRED) {
-                  const double* uc1 = UT + j1 * UTLD;
-                  const double x1 = __shfl_sync(FULLMASK, rhs[bj], 2 * lp + 1) * rd[j1];
-                  const double x0 = fma(-uc1[j0], x1, r0) * rd[j0];
-                  if (lane == 0) {
-                    sol[j0] = x0;
-                    sol[j1] = x1;
-                  }
+            for (int pp = NPAIR - 1; pp >= 0; --pp) {
+              const int j0 = 2 * pp, j1 = j0 + 1, bj = j0 >> 5, l0 = j0 & 31;
+              double rdn0, rdn1, crn, uc0n[D3_RCH], uc1n[D3_RCH];
+              bs_load(pp > 0 ? pp - 1 : 0, rdn0, rdn1, crn, uc0n, uc1n);
+              double rj = rhs[0];
 #pragma unroll
-                  for (int b = 0; b <= bj; ++b) {
-                    const int i = lane + 32 * b;
-                    if (i < j0) rhs[b] = fma(-uc0[i], x0, fma(-uc1[i], x1, rhs[b]));
-                  }
-                } else {
-                  const double x0 = r0 * rd[j0];
-                  if (lane == 0) sol[j0] = x0;
-#pragma unroll
-                  for (int b = 0; b <= bj; ++b) {
-                    const int i = lane + 32 * b;
-                    if (i < j0) rhs[b] = fma(-uc0[i], x0, rhs[b]);
-                  }
+              for (int b = 1; b < D3_RCH; ++b) rj = (bj == b) ? rhs[b] : rj;
+              const double r0 = __shfl_sync(FULLMASK, rj, l0), r1 = __shfl_sync(FULLMASK, rj, l0 + 1);
+              if (j1 < NRED) {
+                const double x1 = r1 * rdc1;
+                const double x0 = fma(-crc, x1, r0) * rdc0;
+                if (lane == 0) {
+                  sol[j0] = x0;
+                  sol[j1] = x1;
                 }
+#pragma unroll
+                for (int b = 0; b < D3_RCH; ++b)
+                  if (lane + 32 * b < j0) rhs[b] = fma(-uc0c[b], x0, fma(-uc1c[b], x1, rhs[b]));
+              } else {
+                const double x0 = r0 * rdc0;
+                if (lane == 0) sol[j0] = x0;
+#pragma unroll
+                for (int b = 0; b < D3_RCH; ++b)
+                  if (lane + 32 * b < j0) rhs[b] = fma(-uc0c[b], x0, rhs[b]);
+              }
+              rdc0 = rdn0;
+              rdc1 = rdn1;
+              crc = crn;
+#pragma unroll
+              for (int b = 0; b < D3_RCH; ++b) {
+                uc0c[b] = uc0n[b];
+                uc1c[b] = uc1n[b];
               }
             }
           }
