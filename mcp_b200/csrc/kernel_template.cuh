@@ -2926,6 +2926,10 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
 // through the same condensation with D = S Y⁻¹, NRHS_SENS right-hand sides per factorisation pass.
 // ------------------------------------------------------------------------------------------------
 #if HAS_JT
+#if FULL_Y   // mode B (∇_y H ≠ 0): the generic forward loop below is the only sensitivity path
+#undef USE_DIRECT_JVP
+#define USE_DIRECT_JVP 0
+#endif
 #ifndef USE_DIRECT_JVP
 #define USE_DIRECT_JVP 1
 #endif
@@ -3012,7 +3016,13 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
     __syncwarp(smask);
     mcp_eval_sens_par(sl, x, y, th, jv, jtv);
     __syncwarp(smask);
+#if FULL_Y
+    // mode B: J_B [Z_x; Z_y] = −[∇_θG; ∇_θH] with J_B = [G_x, G_y; H_x, H_y + diag(s/y)] (the solve kernel's system at
+    // tol = 0: row 3 of src/AutoDiff.jl:27-39 gives Z_s = −(s/y) Z_y); the per-constraint array holds s/y
+    for (int k = sl; k < NY; k += SUB) dinv[k] = s[k] / y[k];
+#else
     for (int k = sl; k < NY; k += SUB) dinv[k] = y[k] / s[k];  // D⁻¹ with D = s/y (tol = 0)
+#endif
     if (p.z_p)
       for (int i = sl; i < NZ * p.P; i += SUB) p.z_p[inst * NZ * p.P + i] = 0.0;
     __syncwarp(smask);
@@ -3125,11 +3135,16 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         for (int e = Q_PTR[q] + sl; e < Q_PTR[q + 1]; e += SUB) {
           const double v = -Q_COEF_AT(e) * opval(Q_CODE[e], jtv, th);
           const int row = Q_ROW[e];
+#if FULL_Y
+          sol[rq * NRED + IPERM[row]] = v;   // (the G and the H rows are both unknowns' rows; row < NX + NY)
+#else
           if (row < NX) sol[rq * NRED + IPERM[row]] = v;
           else wq[rq * NY + (row - NX)] = dinv[row - NX] * v;
+#endif
         }
       }
       __syncwarp(smask);
+#if !FULL_Y
       for (int i = sl; i < NRED; i += SUB) {
         for (int rq = 0; rq < nq; ++rq) {
           double r = sol[rq * NRED + i];
@@ -3139,6 +3154,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
         }
       }
       __syncwarp(smask);
+#endif
       if (band_solve<NRHS_L, L::WS>(W, Cval, UT, sol, rowptr, cpos, jv, th, dinv, S + L::OFF_STAGE, sl, smask)) {
         bad = 1;
         break;
@@ -3156,7 +3172,19 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
           if (p.z_p)
             for (int pp = 0; pp < p.P; ++pp)
               p.z_p[(inst * p.P + pp) * NZ + row] += zx * p.theta_p[(inst * p.P + pp) * NT + q];
+#if FULL_Y
+          if (row >= NX) {   // a y unknown: its s row follows from the complementarity row
+            const int k = row - NX;
+            const double zs = -s[k] * zx / y[k];
+            if (p.dzdtheta) p.dzdtheta[(inst * NT + q) * NZ + NX + NY + k] = zs;
+            if (p.zbar) tb += p.zbar[inst * NZ + NX + NY + k] * zs;
+            if (p.z_p)
+              for (int pp = 0; pp < p.P; ++pp)
+                p.z_p[(inst * p.P + pp) * NZ + NX + NY + k] += zs * p.theta_p[(inst * p.P + pp) * NT + q];
+          }
+#endif
         }
+#if !FULL_Y
         for (int k = sl; k < NY; k += SUB) {
           double hx = 0.0;
           for (int e = H_PTR[k]; e < H_PTR[k + 1]; ++e) hx += H_COEF_AT(e) * opval(H_CODE[e], jv, th) * so[H_COL[e]];
@@ -3174,6 +3202,7 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
               p.z_p[(inst * p.P + pp) * NZ + NX + NY + k] += zs * tp;
             }
         }
+#endif
         if (p.thetabar) {
           tb = sub_sum(tb, smask);
           if (sl == 0) p.thetabar[inst * NT + q] = tb;

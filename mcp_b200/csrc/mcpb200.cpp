@@ -862,10 +862,6 @@ int mcpb200_sensitivities_device(mcpb200_handle h, int64_t B, const double* thet
   (void)eps;  // ∇F_z and ∇F_θ do not depend on ϵ; kept for signature parity with `_solve_jacobian_θ`
   if (!h) return set_err(nullptr, MCPB200_ERR_INVALID_ARGUMENT, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
-  if (h->plan.sens_blocked)
-    return set_err(h, MCPB200_ERR_UNSUPPORTED,
-                   "sensitivities of a problem whose H depends on y (∇_y H ≠ 0) are not implemented: the solve runs in the "
-                   "(nx+ny)-dimensional mode, the sensitivity kernels only know the condensed one");
   if (!h->plan.has_jt)
     return set_err(h, MCPB200_ERR_NO_SENSITIVITIES,
                    "Missing sensitivities. Set `compute_sensitivities = true` when constructing the PrimalDualMCP.");
@@ -1027,10 +1023,6 @@ int mcpb200_sensitivities(mcpb200_handle h, int64_t B, const double* theta, cons
   (void)eps;
   if (!h) return set_err(nullptr, MCPB200_ERR_INVALID_ARGUMENT, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
-  if (h->plan.sens_blocked)
-    return set_err(h, MCPB200_ERR_UNSUPPORTED,
-                   "sensitivities of a problem whose H depends on y (∇_y H ≠ 0) are not implemented: the solve runs in the "
-                   "(nx+ny)-dimensional mode, the sensitivity kernels only know the condensed one");
   if (!h->plan.has_jt)
     return set_err(h, MCPB200_ERR_NO_SENSITIVITIES,
                    "Missing sensitivities. Set `compute_sensitivities = true` when constructing the PrimalDualMCP.");

@@ -886,10 +886,6 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   // the (nx+ny)-dimensional system with only δs eliminated.  MCPB200_FULL_Y=1 forces it (tests).
   P.full_y = !Hy.empty();
   if (const char* e = getenv("MCPB200_FULL_Y")) P.full_y = P.full_y || atoi(e) != 0;
-  if (P.full_y && P.has_jt) {   // the sensitivity kernels implement the condensed mode only
-    P.has_jt = false;
-    P.sens_blocked = true;
-  }
   const int N = P.full_y ? nx + ny : nx;
   P.N = N;
 
@@ -1308,7 +1304,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
   // Adjoint-mode pullback (kernel_template.cuh, mcp_adj_kernel): the forward layout with ONE right-hand side, so
   // far more instances fit an SM than in the forward kernel (lane-change: 4 → 14).  MCPB200_ADJOINT=0 disables it.
-  P.has_adjoint = (P.has_jt && !P.dense_schur && !P.dense_kernel && P.kl == P.ku) ? 1 : 0;
+  P.has_adjoint = (P.has_jt && !P.full_y && !P.dense_schur && !P.dense_kernel && P.kl == P.ku) ? 1 : 0;   // (mode B: forward solves only)
   if (const char* e = getenv("MCPB200_ADJOINT")) P.has_adjoint = P.has_adjoint && atoi(e) != 0;
   int64_t adj_doubles = 0;
   if (P.has_adjoint) {

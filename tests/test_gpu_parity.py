@@ -709,13 +709,43 @@ def test_h_depending_on_y_matches_oracle():
     for tol in (1e-4, 1e-6):
         sol = solve(InteriorPoint(), mcp, Θ, tol=tol)
         compare_batch(mcp, Θ, sol, tol=tol, min_match=1.0)
-    # sensitivities are refused loudly in this mode, never computed wrongly
-    from mcp_b200 import solve_pullback
-    from mcp_b200.capi import MCPB200Error
-    m2 = _lcp_like_mcp(compute_sensitivities=True)
-    s2 = solve(InteriorPoint(), m2, Θ[:, :4])
-    with pytest.raises(MCPB200Error):
-        solve_pullback(m2, s2, Θ[:, :4], 2 * s2.x, None, None)
+
+
+def test_h_depending_on_y_sensitivities():
+    """Sensitivities in the (nx+ny)-dimensional mode (r2): ∂z/∂θ from J_B [Z_x; Z_y] = −[∇_θG; ∇_θH], Z_s = −(s/y) Z_y,
+    against the oracle's QR on the full n×n system (`src/AutoDiff.jl:18-40`); the pullback and the pushforward must
+    be its contractions (`:42-117`), and finite differences of the solve agree."""
+    from mcp_b200 import solve_jacobian_θ, solve_pullback, solve_pushforward
+    mcp = _lcp_like_mcp(compute_sensitivities=True)
+    Θ = np.asfortranarray(np.random.default_rng(9).uniform(-1.0, 2.0, (3, 32)))
+    sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
+    assert np.all(sol.status == 0)
+    J = solve_jacobian_θ(mcp, sol, Θ)
+    g = solve_pullback(mcp, sol, Θ, 2 * sol.x, 2 * sol.y, 3 * sol.s)
+    tp = np.random.default_rng(10).standard_normal((3, 2, 32))
+    xp, yp, sp = solve_pushforward(mcp, sol, Θ, tp)
+    om = OracleMCP(mcp.ir)
+    for b in range(Θ.shape[1]):
+        ref = O.Solution("solved", sol.x[:, b], sol.y[:, b], sol.s[:, b], 0.0, float(sol.ϵ[b]), 0)
+        Jref = O.solve_jacobian_theta(om, ref, Θ[:, b])
+        scale = max(1.0, np.max(np.abs(Jref)))
+        assert np.max(np.abs(J[:, :, b] - Jref)) / scale < SENS_TOL, b
+        zbar = np.concatenate([2 * sol.x[:, b], 2 * sol.y[:, b], 3 * sol.s[:, b]])
+        np.testing.assert_allclose(g[:, b], Jref.T @ zbar, rtol=SENS_TOL, atol=1e-7)
+        np.testing.assert_allclose(np.vstack([xp[:, :, b], yp[:, :, b], sp[:, :, b]]), Jref @ tp[:, :, b], rtol=SENS_TOL, atol=1e-7)
+    # finite differences of the solve itself (tight tolerance so that the ϵ-path contribution is below the bar)
+    h = 1e-5
+    b = 0
+    tight = dict(tol=1e-9)
+    base = solve(InteriorPoint(), mcp, Θ[:, b], **tight)
+    Jb = solve_jacobian_θ(mcp, base, Θ[:, b])
+    for q in range(3):
+        θp, θm = Θ[:, b].copy(), Θ[:, b].copy()
+        θp[q] += h
+        θm[q] -= h
+        sp_, sm_ = solve(InteriorPoint(), mcp, θp, **tight), solve(InteriorPoint(), mcp, θm, **tight)
+        fd = (np.concatenate([sp_.x, sp_.y, sp_.s]) - np.concatenate([sm_.x, sm_.y, sm_.s])) / (2 * h)
+        np.testing.assert_allclose(Jb[:, q], fd, rtol=2e-3, atol=2e-4)
 
 
 def test_full_y_mode_on_lane_change_matches_condensed(lane_game, monkeypatch):
