@@ -258,9 +258,11 @@ def other_workloads(local: int, fp64_peak: float, hbm_gbs: float, reps: int = 3)
     out["cfg1_readme_qp_tol1e-6"], _, _ = solve_entry(mcp, Θ, 1e-6, e2e=False)
     # cfg2 — random convex QP 100×100: cold, then the θ sweep (ϕ ← ϕ + 0.01·N(0,1)) warm-started from the cold solution
     mcp = problems.random_qp(100, 100)
-    Bq = 1 << 14
+    Bq = 1 << 15   # (r1's batch; ≈ 35 ms of the call is the pass-1 tail of the never-converging instances, whatever the batch)
     Θ = problems.random_qp_thetas(Bq, seed=1)
-    cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1")
+    cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1; roofline credits the reference algorithm's flops (dense LU + dense "
+                                                   "Schur product, SURVEY.md §8d) — the kernel executes fewer: LDLᵀ for symmetric G_x, Schur terms "
+                                                   "that are zero in value skipped (DESIGN.md §8)")
     out["cfg2_random_qp_cold"] = cold
     g = torch.Generator(device=dev)
     g.manual_seed(7)
