@@ -2570,7 +2570,11 @@ extern "C" __global__ void __launch_bounds__(SOLVE_LB_THREADS, 1) mcp_solve_kern
   double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * SOLVE_SMEM_DOUBLES;  // my shared-memory block
 #if LARGE_STATE
   double* S = p.state + ((size_t)blockIdx.x * SOLVE_INST + slot) * SOLVE_STATE_DOUBLES;  // vectors in global memory
-  double* W = V;                                                                         // only the window is shared
+#if WIN_GLOBAL
+  double* W = S + SOLVE_OFF_WIN;   // not even one window fits shared memory: it follows the vectors in the global block
+#else
+  double* W = V;                   // only the window is shared
+#endif
 #else
   double* S = V;
   double* W = V + SOLVE_OFF_WIN;
@@ -2978,7 +2982,11 @@ __device__ __forceinline__ void sens_body(const SensParams& p) {
   double* V = smem + SHARED_TABLE_DOUBLES + (size_t)slot * L::SMEM;
 #if LARGE_STATE
   double* S = p.state + ((size_t)blockIdx.x * L::INST + slot) * L::STATE;
+#if WIN_GLOBAL
+  double* W = S + L::OFF_WIN;
+#else
   double* W = V;
+#endif
 #else
   double* S = V;
   double* W = V + L::OFF_WIN;

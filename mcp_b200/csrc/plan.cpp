@@ -1248,7 +1248,24 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     }
   }
   int sol_in_smem = 0;
-  if (P.large_state) {
+  // Window in global memory: when not even ONE instance's factorisation window fits shared memory (a dense problem of a
+  // few hundred unknowns, a band of a few hundred rows) the window moves to the instance's L2-resident global block as
+  // well — the same code on a generic pointer, an order of magnitude slower per pivot step than the shared-memory
+  // window, but the problem is solved instead of refused.  MCPB200_WIN_GLOBAL=1 forces it (tests).
+  int win_global = 0;
+  if (!P.dense_kernel && !P.tiny_kernel) {
+    const bool nofit = warps_for(even(win_solve)) < 1 || (P.has_jt && warps_for(even(win_sens)) < 1);
+    if (nofit) win_global = 1;
+    if (const char* e = getenv("MCPB200_WIN_GLOBAL")) win_global = (atoi(e) != 0) || nofit;
+    if (win_global) P.large_state = 1;
+  }
+  if (P.large_state && win_global) {
+    solve_doubles = 2;   // nothing of an instance lives in shared memory (the per-CTA tables still do)
+    sens_doubles = 2;
+    P.state_doubles_solve = even(solve_state) + even(win_solve) + 2;
+    P.state_doubles_sens = even(sens_state) + even(win_sens) + 2;
+    ls_cap = std::min(ls_cap, 4);
+  } else if (P.large_state) {
     solve_doubles = even(win_solve);
     // δx / the right-hand side is read and written once per pivot step and once per back-substitution step: keep it
     // in shared memory next to the window when that does not cost an instance (masked game N = 4: 9.6 KB)
@@ -1286,6 +1303,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     if (!regwin_used && !P.dense_schur) {
       P.nwide = std::max(1, std::min({4, 16 / P.ipc_solve, nbatch}));
       if (const char* e = getenv("MCPB200_NWIDE")) P.nwide = std::max(1, std::min({atoi(e), nbatch, 32 / P.ipc_solve}));
+      if (win_global) P.nwide = 1;   // (the helpers' mailbox sits behind a shared-memory window)
       // the helpers of instance slot k meet at named barrier 1 + k: ids 1 … 15 exist (0 is __syncthreads)
       if (P.nwide > 1 && P.ipc_solve > 15) P.nwide = 1;
     }
@@ -1304,7 +1322,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   P.smem_solve = (shared_table_doubles + solve_doubles * P.ipc_solve) * 8;
   // Adjoint-mode pullback (kernel_template.cuh, mcp_adj_kernel): the forward layout with ONE right-hand side, so
   // far more instances fit an SM than in the forward kernel (lane-change: 4 → 14).  MCPB200_ADJOINT=0 disables it.
-  P.has_adjoint = (P.has_jt && !P.full_y && !P.dense_schur && !P.dense_kernel && P.kl == P.ku) ? 1 : 0;   // (mode B: forward solves only)
+  P.has_adjoint = (P.has_jt && !P.full_y && !win_global && !P.dense_schur && !P.dense_kernel && P.kl == P.ku) ? 1 : 0;   // (mode B: forward solves only)
   if (const char* e = getenv("MCPB200_ADJOINT")) P.has_adjoint = P.has_adjoint && atoi(e) != 0;
   int64_t adj_doubles = 0;
   if (P.has_adjoint) {
@@ -1486,6 +1504,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   os << "#define DENSE_KERNEL " << P.dense_kernel << "\n#define LARGE_STATE " << P.large_state << "\n";
   os << "#define FULL_Y " << P.full_y << "\n#define S_GLOBAL " << s_global << "\n";
   os << "#define TINY_KERNEL " << P.tiny_kernel << "\n";
+  os << "#define WIN_GLOBAL " << win_global << "\n";
   os << "#define NWIDE " << P.nwide << "\n#define SOL_IN_SMEM " << sol_in_smem << "\n#define REGWIN_PW_MAX " << regwin_pw_max << "\n";
   os << "#define SOLVE_STATE_DOUBLES " << P.state_doubles_solve << "\n#define SENS_STATE_DOUBLES " << P.state_doubles_sens << "\n";
   os << "#define DENSE_SCHUR " << P.dense_schur << "\n#define STAGE_N " << stage_n << "\n";

@@ -359,6 +359,20 @@ def test_dense_symmetric_path_and_fallbacks():
     assert n >= 6
 
 
+def test_dense_problem_beyond_one_cta():
+    """A dense condensed system whose factorisation window (200 × 202 doubles = 323 KB) does not fit the shared memory
+    of one SM: r1 refused it (`MCPB200_ERR_UNSUPPORTED`); the window now moves to the instance's global block next to
+    its vectors (slow, but solved) — same parity bar against the C oracle."""
+    from mcp_b200.solver import _handle
+    n, m = 200, 120
+    mcp = problems.random_qp(n, m)
+    info = _handle(mcp).info()
+    assert info["n_reduced"] == n and info["window_rows"] == n
+    Θ = problems.random_qp_thetas(6, seed=31, num_primals=n, num_inequalities=m)
+    _, solved = _qp_vs_c_oracle(mcp, Θ)
+    assert solved >= 4
+
+
 def test_random_qp_batch_properties():
     """cfg2 at a batch the oracle cannot follow (every CTA solves several instances back to back, both passes run):
     size-independent checks on ALL instances with the QP's own data — stationarity M x − ϕ − Aᵀy, primal
