@@ -1116,7 +1116,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   const int64_t nterms_all = (int64_t)P.t_coef.size();
   const int uts = (P.WC + 1) & ~1;   // UT row stride: even ⇒ 16-byte rows for cp.async.cg
   // widest register-window part (entries of one window row held by one lane); MCPB200_REGWIN_PW overrides
-  int regwin_pw_max = 40;
+  int regwin_pw_max = 48;   // (48: the masked game at N = 4 — 46 entries per lane, 254 registers at 256 threads per SM, no spills — r2: pass 0 −19 %, tail −7 %)
   if (const char* e = getenv("MCPB200_REGWIN_PW")) regwin_pw_max = std::max(2, atoi(e));
   // Geometry of the register-resident window — mirrors BS_NPART / BS_PW / BS_REGWIN of kernel_template.cuh: WR + 1 row
   // slots (one spare, so the entering row is staged a step early), NPART lanes per row, PW positions per lane covering
@@ -1287,6 +1287,11 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   }
   P.ipc_solve = warps_for(solve_doubles);
   if (!P.large_state && !P.dense_kernel && !P.tiny_kernel && P.sub == 32) P.ipc_solve = quad(P.ipc_solve);
+  {
+    // a register window wider than 40 entries per lane needs ≈ 250 registers per thread: at most 256 threads per CTA
+    int npart, pw;
+    if (!P.dense_kernel && !P.tiny_kernel && regwin_geom(npart, pw) && pw > 40) P.ipc_solve = std::min(P.ipc_solve, 256 / P.sub);
+  }
   P.ipc_sens = P.has_jt ? warps_for(sens_doubles) : 1;
   if (P.large_state) {
     P.ipc_solve = std::min(P.ipc_solve, ls_cap);
