@@ -6,6 +6,7 @@ relative distance of each FP64 implementation from the extended-precision trajec
 
     python scripts/adjudicate_parity.py masked  [--B 256] [--all]     # cfg4 N = 4, the 8 masks × 32 scenarios of the test
     python scripts/adjudicate_parity.py lane    [--B 64]
+    python scripts/adjudicate_parity.py qp      [--B 64] --all         # cfg2 QP 100×100: the GPU runs LDLᵀ, the oracles pivoted LU
 Output: gpurun_out/adjudicate_<name>.json
 """
 import argparse
@@ -36,6 +37,8 @@ _G = {}
 def _setup(which):
     if which == "masked":
         mcp = problems.masked_game(4, 30).mcp
+    elif which == "qp":
+        mcp = problems.random_qp(100, 100)
     else:
         mcp = problems.lane_change_game().mcp
     _G["mcp"] = mcp
@@ -55,7 +58,7 @@ def _ext_one(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["masked", "lane"])
+    ap.add_argument("which", choices=["masked", "lane", "qp"])
     ap.add_argument("--B", type=int, default=0)
     ap.add_argument("--all", action="store_true", help="run the extended oracle on every instance, not only suspects")
     ap.add_argument("--workers", type=int, default=os.cpu_count())
@@ -65,6 +68,11 @@ def main():
         mcp = problems.masked_game(4, 30).mcp
         Θ = problems.masked_game_thetas(B, 4, seed=11)          # tests/test_gpu_parity.py::test_masked_game_parity_statistics
         x0 = problems.masked_game_x0(Θ, 4, 30)
+    elif a.which == "qp":
+        B, tol = a.B or 64, 1e-6
+        mcp = problems.random_qp(100, 100)
+        Θ = problems.random_qp_thetas(B, seed=11)               # ::test_dense_symmetric_path_and_fallbacks (first B)
+        x0 = None
     else:
         B, tol = a.B or 64, 1e-6
         mcp = problems.lane_change_game().mcp
