@@ -136,7 +136,7 @@ def test_sensitivities_lane_change(lane_game):
     """cfg5: batched ∂z/∂θ on well-posed instances (moving start, see `problems.lane_change_thetas`)."""
     from mcp_b200 import solve_jacobian_θ, solve_pullback
     mcp = lane_game.mcp
-    Θ = problems.lane_change_thetas(8, seed=5, moving=True)
+    Θ = problems.lane_change_thetas(24, seed=5, moving=True)
     sol = solve(InteriorPoint(), mcp, Θ, tol=1e-6)
     J = solve_jacobian_θ(mcp, sol, Θ)
     zbar = np.concatenate([2 * sol.x, 2 * sol.y, 0 * sol.s], axis=0)
@@ -153,7 +153,7 @@ def test_sensitivities_lane_change(lane_game):
         gref = Jref.T @ zbar[:, b]
         assert np.max(np.abs(g[:, b] - gref)) / max(1.0, np.max(np.abs(gref))) < SENS_TOL
         checked += 1
-    assert checked >= 4
+    assert checked >= 16
 
 
 def test_adjoint_pullback_matches_forward(monkeypatch):
@@ -565,12 +565,19 @@ def test_masked_game_jacobian_consistency():
     for b in np.nonzero(sol.status == 0)[0]:
         gref = J[:, :, b].T @ zbar[:, b]
         assert np.max(np.abs(g[:, b] - gref)) / max(1.0, np.max(np.abs(gref))) < SENS_TOL
-    b = int(np.nonzero(sol.status == 0)[0][0])
-    Jz = om.JFz(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
-    Jt = om.JFt(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
-    R = Jz @ J[:, :, b] + (Jt.toarray() if hasattr(Jt, "toarray") else Jt)
-    scale = abs(Jz).max() * max(1.0, np.abs(J[:, :, b]).max())
-    assert np.max(np.abs(R)) / scale < 1e-9, np.max(np.abs(R)) / scale
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    for b in np.nonzero(sol.status == 0)[0]:      # every solved instance (r1 checked one)
+        Jz = om.JFz(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
+        Jt = om.JFt(sol.x[:, b], sol.y[:, b], sol.s[:, b], Θ[:, b], float(sol.ϵ[b]))
+        Jt = Jt.toarray() if hasattr(Jt, "toarray") else np.asarray(Jt)
+        R = Jz @ J[:, :, b] + Jt
+        scale = abs(Jz).max() * max(1.0, np.abs(J[:, :, b]).max())
+        assert np.max(np.abs(R)) / scale < 1e-9, (b, np.max(np.abs(R)) / scale)
+        # … and entry-wise against the oracle's own solve of ∇F_z X = −∇F_θ on the full 4140-dimensional system (sparse LU
+        # in the role of the reference's QR, `src/AutoDiff.jl:27-39`; the matrix is well conditioned at these points)
+        Jref = spla.splu(sp.csc_matrix(Jz)).solve(-Jt)
+        assert np.max(np.abs(J[:, :, b] - Jref)) / max(1.0, np.max(np.abs(Jref))) < SENS_TOL, b
 
 
 def test_lane_change_parity_statistics(lane_game):
