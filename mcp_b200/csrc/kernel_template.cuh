@@ -141,6 +141,7 @@ template <int NRHS = 1>
 __device__ __forceinline__ void load_shared_tables(double* smem_base, bool transposed = false) {
   int* rowptr = reinterpret_cast<int*>(smem_base);
   unsigned short* cpos = reinterpret_cast<unsigned short*>(rowptr + NRED + 1);
+  LOAD_HOT_TABLES();   // (plan.cpp, HotTables: the per-step index / coefficient tables → static shared memory, when they fit)
 #if HAS_ADJOINT
   if (transposed) {   // the column-major view of the same non-zeros: the factorisation then sees Cᵀ
     for (int i = threadIdx.x; i <= NRED; i += blockDim.x) rowptr[i] = DT_ROWPTR[i];

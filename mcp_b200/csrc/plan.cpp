@@ -265,10 +265,41 @@ bool wide_tables() {
   return e && atoi(e) != 0;
 }
 
+// Hot tables (r2): the index / coefficient tables every warp walks once per Newton step — assembly, condensed right-hand
+// side, recovery of δy — can live in STATIC shared memory, copied from their global image when a kernel starts
+// (LOAD_HOT_TABLES in load_shared_tables), when that costs no resident instance: the lane-change plan leaves 19 KB of
+// the SM's shared memory unused and these tables are 14 KB.  A table named in g_hot.names is then emitted as NAME_G
+// (global) plus `__shared__ T NAME[n]`, so the kernels' accesses need no change.
+struct HotTables {
+  bool on = false;
+  std::vector<std::string> names;
+  std::ostringstream copy;
+  size_t bytes = 0;
+  bool has(const std::string& n) const { return on && std::find(names.begin(), names.end(), n) != names.end(); }
+};
+thread_local HotTables g_hot;
+
+size_t hot_elem_size(const std::string& type) {
+  if (type == "short" || type == "unsigned short") return 2;
+  if (type == "unsigned char") return 1;
+  if (type == "double") return 8;
+  return 4;   // int, float
+}
+
 template <class T>
 void emit_raw_table(std::ostringstream& os, const char* type, const std::string& name, const std::vector<T>& v, bool is_double = false,
                     bool is_float = false) {
-  os << "__device__ const " << type << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+  std::string base = name;   // NAME_IDX / NAME_VAL of a dictionary table belong to NAME
+  for (const char* suf : {"_IDX", "_VAL"})
+    if (base.size() > 4 && base.compare(base.size() - 4, 4, suf) == 0) base = base.substr(0, base.size() - 4);
+  const bool hot = g_hot.has(base);
+  const size_t n = std::max<size_t>(v.size(), 1);
+  if (hot) {
+    os << "__shared__ " << type << " " << name << "[" << n << "];\n";
+    g_hot.copy << "  for (int i_ = threadIdx.x; i_ < " << n << "; i_ += blockDim.x) " << name << "[i_] = " << name << "_G[i_]; \\\n";
+    g_hot.bytes += (n * hot_elem_size(type) + 15) & ~size_t(15);
+  }
+  os << "__device__ const " << type << " " << name << (hot ? "_G" : "") << "[" << std::max<size_t>(v.size(), 1) << "] = {";
   if (v.empty()) os << "0";
   for (size_t i = 0; i < v.size(); ++i) {
     if (i) os << ",";
@@ -1194,8 +1225,78 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
   layout_sens();
   const int64_t nd = (int64_t)P.d_row.size();
   const int64_t shared_table_doubles = even(((int64_t)(N + 1) * 4 + nd * 2 + 7) / 8);
+  // Hot tables in static shared memory (see HotTables): sized here with the emitter's own narrowing rules, enabled when
+  // the standard layout keeps its number of resident instances with the tables beside it.  MCPB200_HOT_SMEM=0 disables.
+  g_hot = HotTables{};
+  int64_t hot_reserve = 0;
+  {
+    auto int_bytes = [&](const std::vector<int32_t>& v) -> int64_t {
+      bool narrow = !wide_tables();
+      for (size_t i = 0; i < v.size() && narrow; ++i) narrow = v[i] >= -32768 && v[i] <= 32767;
+      return (int64_t)((std::max<size_t>(v.size(), 1) * (narrow ? 2 : 4) + 15) & ~size_t(15));
+    };
+    auto dbl_bytes = [&](const std::vector<double>& v) -> int64_t {
+      bool all_float = !wide_tables(), finite = true;
+      std::set<unsigned long long> distinct;
+      for (double d : v) {
+        if (!std::isfinite(d)) finite = false;
+        if (!((double)(float)d == d)) all_float = false;
+        unsigned long long bits;
+        memcpy(&bits, &d, 8);
+        distinct.insert(bits);
+      }
+      const size_t n = std::max<size_t>(v.size(), 1);
+      if (all_float && finite) return (int64_t)((n * 4 + 15) & ~size_t(15));
+      if (!wide_tables() && distinct.size() <= 256 && v.size() > 64)
+        return (int64_t)(((n + 15) & ~size_t(15)) + ((std::max<size_t>(distinct.size(), 1) * 8 + 15) & ~size_t(15)));
+      return (int64_t)((n * 8 + 15) & ~size_t(15));
+    };
+    bool ti16 = !wide_tables();
+    for (size_t i = 0; i < P.t_a.size() && ti16; ++i)
+      ti16 = std::abs(P.t_a[i]) < 32767 && std::abs(P.t_b[i]) < 32767 && std::abs(P.t_k[i]) < 32767;
+    const bool tp16 = !wide_tables() && !P.d_tptr.empty() && P.d_tptr.back() < 32768;
+    int64_t est = 0;
+    est += (int64_t)((std::max<size_t>(P.d_tptr.size(), 1) * (tp16 ? 2 : 4) + 15) & ~size_t(15));
+    est += dbl_bytes(P.d_base) + dbl_bytes(P.t_coef);
+    est += (int64_t)((std::max<size_t>(P.t_a.size(), 1) * (ti16 ? 8 : 16) + 15) & ~size_t(15));
+    est += int_bytes(P.r_ptr) + int_bytes(P.r_code) + int_bytes(P.r_k) + dbl_bytes(P.r_coef);
+    est += int_bytes(P.h_ptr) + int_bytes(P.h_code) + int_bytes(P.h_col) + dbl_bytes(P.h_coef);
+    est += int_bytes(P.perm) + int_bytes(P.iperm);
+    est += 256;
+    int64_t hot_cap = 40 * 1024;   // (static shared memory is limited to 48 KB per kernel)
+    if (const char* e = getenv("MCPB200_HOT_CAP")) hot_cap = atoll(e);
+    bool want = !P.dense_kernel && !P.dense_schur && !P.tiny_kernel && !P.full_y && est <= hot_cap;
+    if (const char* e = getenv("MCPB200_HOT_SMEM")) want = want && atoi(e) != 0;
+    if (want) {
+      // same number of instances per CTA with and without the reserve (whole quads of warps above 16, as below)?
+      auto inst = [&](int64_t reserve) {
+        int64_t w = (kSmemBudget - shared_table_doubles * 8 - reserve) / (solve_doubles * 8);
+        w = std::min<int64_t>(w, 768 / P.sub);
+        if (P.sub == 16) w &= ~int64_t(1);
+        if (P.sub == 32 && w > 16) w = (w / 4) * 4;
+        return w;
+      };
+      // … or, for plans that will keep only the window in shared memory (large-state mode, decided below with the
+      // same counts), the same number of windows up to that mode's cap
+      auto wins = [&](int64_t reserve, int64_t doubles) {
+        return std::max<int64_t>(0, std::min<int64_t>((kSmemBudget - shared_table_doubles * 8 - reserve) / (doubles * 8), 768 / P.sub));
+      };
+      int64_t cap_ls = 8;
+      if (const char* e = getenv("MCPB200_LS_WARPS")) cap_ls = std::max(1, atoi(e));
+      const int64_t ls_doubles = even(win_solve) + even(N);
+      const bool would_ls = inst(0) < 1 || (inst(0) < 4 && std::min(cap_ls, wins(0, even(win_solve))) >= 2 * inst(0));
+      const bool std_ok = inst(0) >= 1 && inst(est) == inst(0);
+      const bool ls_ok = wins(est, ls_doubles) >= 1 && std::min(cap_ls, wins(est, ls_doubles)) == std::min(cap_ls, wins(0, ls_doubles));
+      if (would_ls ? ls_ok : std_ok) {
+        g_hot.on = true;
+        g_hot.names = {"D_TP", "D_BASE", "T_COEF", "T_I", "R_PTR", "R_CODE", "R_K", "R_COEF", "H_PTR", "H_CODE", "H_COL", "H_COEF",
+                       "PERM", "IPERM"};
+        hot_reserve = est;
+      }
+    }
+  }
   auto warps_for = [&](int64_t doubles) {  // instances per CTA
-    int64_t w = (kSmemBudget - shared_table_doubles * 8) / (doubles * 8);
+    int64_t w = (kSmemBudget - shared_table_doubles * 8 - hot_reserve) / (doubles * 8);
     w = std::min<int64_t>(w, 768 / P.sub);   // ≤ 768 threads per CTA keeps ≥ 85 registers per thread
     if (const char* e = getenv("MCPB200_MAX_WARPS")) w = std::min<int64_t>(w, std::max(1, atoi(e)));   // tuning: fewer instances, more L1
     if (P.sub == 16) w &= ~int64_t(1);       // whole warps
@@ -1560,7 +1661,14 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     for (size_t i = 0; i < P.t_a.size() && ti16; ++i)
       ti16 = std::abs(P.t_a[i]) < 32767 && std::abs(P.t_b[i]) < 32767 && std::abs(P.t_k[i]) < 32767;
     os << "typedef " << (ti16 ? "short4" : "int4") << " TI_T;\n";
-    os << "__device__ const TI_T T_I[" << std::max<size_t>(P.t_a.size(), 1) << "] = {";
+    const bool ti_hot = g_hot.has("T_I");
+    if (ti_hot) {
+      const size_t n = std::max<size_t>(P.t_a.size(), 1);
+      os << "__shared__ TI_T T_I[" << n << "];\n";
+      g_hot.copy << "  for (int i_ = threadIdx.x; i_ < " << n << "; i_ += blockDim.x) T_I[i_] = T_I_G[i_]; \\\n";
+      g_hot.bytes += (n * (ti16 ? 8 : 16) + 15) & ~size_t(15);
+    }
+    os << "__device__ const TI_T " << (ti_hot ? "T_I_G" : "T_I") << "[" << std::max<size_t>(P.t_a.size(), 1) << "] = {";
     if (P.t_a.empty()) os << "{0,0,0,0}";
     for (size_t i = 0; i < P.t_a.size(); ++i) {
       if (i) os << ",";
@@ -1592,6 +1700,9 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     emit_table(os, "int", "Q_CODE", P.q_code);
     emit_table(os, "double", "Q_COEF", P.q_coef, true);
   }
+  if (g_hot.on && (int64_t)g_hot.bytes > hot_reserve) return fail(MCPB200_ERR_INTERNAL, "hot-table shared memory under-estimated");
+  os << "#define HOT_SMEM " << (g_hot.on ? 1 : 0) << "\n#define LOAD_HOT_TABLES() do { \\\n" << g_hot.copy.str() << "} while (0)\n";
+  P.hot_smem_bytes = g_hot.on ? (int)g_hot.bytes : 0;
   const std::string powi_src =
       "__device__ __forceinline__ double mcp_powi(double a, int n) {\n"
       "  double r = 1.0; bool neg = n < 0; if (neg) n = -n;\n"

@@ -87,6 +87,7 @@ struct Plan {
   int sub = 32;                       // lanes per instance (16: two instances per warp)
   int regwin = 0;                     // window rows in registers (shuffle broadcast) instead of shared memory
   int ipc_solve = 1, ipc_sens = 1;    // instances (warps) per CTA
+  int hot_smem_bytes = 0;             // static shared memory of the hot tables (0: they stay in global memory)
   int has_adjoint = 0, ipc_adj = 1;   // adjoint-mode pullback kernel (one right-hand side: its own, denser layout)
   int64_t smem_adj = 0, state_doubles_adj = 0;
   int nwide = 1;                      // warps cooperating on one instance's window sweep (solve kernel, shared-memory window)
