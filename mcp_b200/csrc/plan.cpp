@@ -1262,7 +1262,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     est += int_bytes(P.r_ptr) + int_bytes(P.r_code) + int_bytes(P.r_k) + dbl_bytes(P.r_coef);
     est += int_bytes(P.h_ptr) + int_bytes(P.h_code) + int_bytes(P.h_col) + dbl_bytes(P.h_coef);
     est += int_bytes(P.perm) + int_bytes(P.iperm);
-    est += 256;
+    est += 256 + 2 * 64;   // (+ the chunk tables of the two-phase assembly, a handful of entries)
     int64_t hot_cap = 40 * 1024;   // (static shared memory is limited to 48 KB per kernel)
     if (const char* e = getenv("MCPB200_HOT_CAP")) hot_cap = atoll(e);
     bool want = !P.dense_kernel && !P.dense_schur && !P.tiny_kernel && !P.full_y && est <= hot_cap;
@@ -1290,7 +1290,7 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
       if (would_ls ? ls_ok : std_ok) {
         g_hot.on = true;
         g_hot.names = {"D_TP", "D_BASE", "T_COEF", "T_I", "R_PTR", "R_CODE", "R_K", "R_COEF", "H_PTR", "H_CODE", "H_COL", "H_COEF",
-                       "PERM", "IPERM"};
+                       "PERM", "IPERM", "CH_D", "CH_T"};
         hot_reserve = est;
       }
     }

@@ -86,12 +86,14 @@ def test_invalid_ir_is_rejected():
 
 def test_h_depending_on_y_compiles_in_full_y_mode():
     """∇_y H ≠ 0 (the reference accepts any H(x, y; θ), `src/mcp.jl:27-52,76-80`): the plan switches to the
-    (nx+ny)-dimensional system with only δs eliminated; sensitivities are not generated in that mode."""
+    (nx+ny)-dimensional system with only δs eliminated; sensitivities (r2) are forward solves of the same system — no
+    adjoint kernel in that mode."""
     mcp = PrimalDualMCP(lambda x, y, θ: x - θ - y, lambda x, y, θ: x + 0.5 * y, unconstrained_dimension=1,
                         constrained_dimension=1, parameter_dimension=1)
     h = capi.Handle(mcp.ir, capi.COMPILE_ONLY)
     src, info = h.source(), h.info()
-    assert _macros(src)["FULL_Y"] == "1" and info["n_reduced"] == 2 and info["has_sensitivities"] == 0
+    assert _macros(src)["FULL_Y"] == "1" and info["n_reduced"] == 2 and info["has_sensitivities"] == 1
+    assert _macros(src)["HAS_ADJOINT"] == "0"
     h.close()
     # a problem of the reference's own structure stays in the condensed mode
     h = capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY)
@@ -214,6 +216,14 @@ def test_cooperative_instances_are_planned_for_big_windows(monkeypatch, tmp_path
     """Plans whose window stays in shared memory (too wide for the register layout) get NWIDE warps per instance;
     register-window plans and tiny problems keep one (sub-)warp per instance."""
     monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    # r2: the masked game at N = 4 (46 window entries per lane) is inside the register-window limit of 48 — one warp
+    # per instance, at most 256 threads per CTA (≈ 250 registers per thread)
+    h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
+    m = _macros(h.source())
+    assert (m["NWIDE"], m["LARGE_STATE"], m["SUB"]) == ("1", "1", "32")
+    assert h.info()["threads_per_instance"] == 32 and h.info()["instances_per_cta"] == 8
+    # with the r1 limit its window stays in shared memory and gets helper warps
+    monkeypatch.setenv("MCPB200_REGWIN_PW", "40")
     h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
     m = _macros(h.source())
     assert (m["NWIDE"], m["LARGE_STATE"], m["SUB"]) == ("2", "1", "32")
@@ -224,6 +234,29 @@ def test_cooperative_instances_are_planned_for_big_windows(monkeypatch, tmp_path
     monkeypatch.setenv("MCPB200_NWIDE", "1")
     h = capi.Handle(problems.masked_game(4, 30).mcp.ir, capi.COMPILE_ONLY)
     assert _macros(h.source())["NWIDE"] == "1" and h.info()["threads_per_instance"] == 32
+
+
+def test_hot_tables_move_to_shared_memory_when_it_costs_no_instance(monkeypatch, tmp_path):
+    """r2: the per-step index / coefficient tables become `__shared__` arrays (filled from a global image `NAME_G` by
+    LOAD_HOT_TABLES) when the plan keeps its resident instances with them: the lane-change plan (16 instances + 14.5 KB
+    of tables); not the masked game (tables beyond the 48 KB static limit), not the dense kernels."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    h = capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY)
+    src, info = h.source(), h.info()
+    assert _macros(src)["HOT_SMEM"] == "1" and info["instances_per_cta"] == 16
+    for name in ("D_TP", "T_COEF", "R_PTR", "R_COEF", "H_COL", "PERM"):
+        assert re.search(r"^__shared__ \w[\w ]* %s\[\d+\];$" % name, src, flags=re.M), name
+        assert re.search(r"^__device__ const \w[\w ]* %s_G\[\d+\] = " % name, src, flags=re.M), name
+        assert "%s[i_] = %s_G[i_];" % (name, name) in src
+    assert re.search(r"^__shared__ TI_T T_I\[\d+\];$", src, flags=re.M)
+    assert "__shared__ short D_CPOS" not in src           # (already copied into the dynamic block by load_shared_tables)
+    monkeypatch.setenv("MCPB200_HOT_SMEM", "0")
+    h = capi.Handle(problems.lane_change_game().mcp.ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["HOT_SMEM"] == "0" and "__shared__ short D_TP" not in h.source()
+    assert h.info()["instances_per_cta"] == 16
+    monkeypatch.delenv("MCPB200_HOT_SMEM")
+    assert _macros(capi.Handle(problems.random_qp(12, 10).ir, capi.COMPILE_ONLY).source())["HOT_SMEM"] == "0"
+    assert _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())["HOT_SMEM"] == "0"
 
 
 def test_split_units_respect_the_kernels_register_budget(monkeypatch, tmp_path):
