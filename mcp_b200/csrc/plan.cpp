@@ -275,6 +275,10 @@ struct HotTables {
   std::vector<std::string> names;
   std::ostringstream copy;
   size_t bytes = 0;
+  // tables whose name starts with `prefix` (the leaf-index tables of the shape-grouped evaluation, sized only at emission)
+  // follow while `room` bytes of the SM's shared memory are left beside the kernels' dynamic blocks
+  std::string prefix;
+  int64_t room = 0;
   bool has(const std::string& n) const { return on && std::find(names.begin(), names.end(), n) != names.end(); }
 };
 thread_local HotTables g_hot;
@@ -292,8 +296,15 @@ void emit_raw_table(std::ostringstream& os, const char* type, const std::string&
   std::string base = name;   // NAME_IDX / NAME_VAL of a dictionary table belong to NAME
   for (const char* suf : {"_IDX", "_VAL"})
     if (base.size() > 4 && base.compare(base.size() - 4, 4, suf) == 0) base = base.substr(0, base.size() - 4);
-  const bool hot = g_hot.has(base);
+  bool hot = g_hot.has(base);
   const size_t n = std::max<size_t>(v.size(), 1);
+  if (!hot && g_hot.on && g_hot.room > 0 && !g_hot.prefix.empty() && name.rfind(g_hot.prefix, 0) == 0) {
+    const int64_t sz = (int64_t)((n * hot_elem_size(type) + 15) & ~size_t(15));
+    if (sz <= g_hot.room) {
+      hot = true;
+      g_hot.room -= sz;
+    }
+  }
   if (hot) {
     os << "__shared__ " << type << " " << name << "[" << n << "];\n";
     g_hot.copy << "  for (int i_ = threadIdx.x; i_ < " << n << "; i_ += blockDim.x) " << name << "[i_] = " << name << "_G[i_]; \\\n";
@@ -1701,8 +1712,12 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
     emit_table(os, "double", "Q_COEF", P.q_coef, true);
   }
   if (g_hot.on && (int64_t)g_hot.bytes > hot_reserve) return fail(MCPB200_ERR_INTERNAL, "hot-table shared memory under-estimated");
-  os << "#define HOT_SMEM " << (g_hot.on ? 1 : 0) << "\n#define LOAD_HOT_TABLES() do { \\\n" << g_hot.copy.str() << "} while (0)\n";
-  P.hot_smem_bytes = g_hot.on ? (int)g_hot.bytes : 0;
+  const int64_t max_dynamic = std::max<int64_t>({(int64_t)P.smem_solve, P.has_jt ? (int64_t)P.smem_sens : 0, P.has_adjoint ? (int64_t)P.smem_adj : 0});
+  if (g_hot.on) {   // what is left goes to the evaluation's leaf-index tables, in emission order
+    g_hot.prefix = "mcp_eval_newton_s";
+    g_hot.room = std::min<int64_t>(kSmemBudget - max_dynamic - (int64_t)g_hot.bytes - 128, 46 * 1024 - (int64_t)g_hot.bytes);
+    if (const char* e = getenv("MCPB200_HOT_EVAL")) if (atoi(e) == 0) g_hot.room = 0;
+  }
   const std::string powi_src =
       "__device__ __forceinline__ double mcp_powi(double a, int n) {\n"
       "  double r = 1.0; bool neg = n < 0; if (neg) n = -n;\n"
@@ -1753,6 +1768,10 @@ int build_plan(const mcpb200_problem_desc& d, const std::string& kernel_template
                    "x, y, th, jv, jtv", outs, {"jv", "jtv"}, P.sub, &P.units, unit_prelude, use_shapes);
     }
   }
+  g_hot.room = 0;
+  if (g_hot.on && max_dynamic + (int64_t)g_hot.bytes > kSmemBudget) return fail(MCPB200_ERR_INTERNAL, "hot tables exceed the shared memory of one SM");
+  os << "#define HOT_SMEM " << (g_hot.on ? 1 : 0) << "\n#define LOAD_HOT_TABLES() do { \\\n" << g_hot.copy.str() << "} while (0)\n";
+  P.hot_smem_bytes = g_hot.on ? (int)g_hot.bytes : 0;
   if (P.tiny_kernel) {
     auto val = [&](int code) -> std::string {
       if (code == -1) return "1.0";
