@@ -136,7 +136,11 @@ typedef struct mcpb200_problem* mcpb200_handle;
 /* ---- lifecycle --------------------------------------------------------------------------- */
 
 /* Replaces the code-generation half of the PrimalDualMCP constructors (src/mcp.jl:55-150): analyses the
- * IR, builds the condensed-system assembly tables, generates CUDA source and compiles it for sm_100a. */
+ * IR, builds the condensed-system assembly tables, generates CUDA source and compiles it for sm_100a.
+ * Any H(x, y; θ) the reference accepts is accepted (∇_y H ≠ 0 switches to the (nx+ny)-dimensional system,
+ * sensitivities included); a factorisation window too large for one SM's shared memory moves to global
+ * memory (slow, not refused).  MCPB200_ERR_UNSUPPORTED remains for one case: a condensed system whose
+ * ordered bandwidth needs more than 256 window rows. */
 int mcpb200_create(const mcpb200_problem_desc* desc, uint32_t flags, mcpb200_handle* out);
 int mcpb200_destroy(mcpb200_handle h);
 const char* mcpb200_last_error(mcpb200_handle h);
