@@ -68,7 +68,27 @@ def main():
         s=np.stack([s.s for s in sols], axis=1), eps=np.array([s.eps for s in sols]),
         outer_iters=np.array([s.outer_iters for s in sols], dtype=np.int32),
         newton_steps=np.array([s.newton_steps for s in sols], dtype=np.int32))
+    qp100_golden()
     print("golden vectors written to", HERE)
+
+
+def qp100_golden():
+    """cfg2 at the benchmark's own size (100 primals, 100 inequalities, θ of 20 200 entries).  θ is NOT stored (646 KB for
+    four instances): it is regenerated from the seed by `problems.random_qp_thetas` and guarded by its SHA-256."""
+    import hashlib
+    qp = problems.random_qp(100, 100)
+    oq = OracleMCP(qp.ir)
+    seed, B = 5, 4
+    Θ = problems.random_qp_thetas(B, seed=seed)
+    sols = [O.solve_interior_point(oq, Θ[:, b], tol=1e-6) for b in range(B)]
+    np.savez_compressed(
+        os.path.join(HERE, "random_qp_100x100_seed5.npz"), seed=seed, B=B, tol=1e-6,
+        theta_sha256=hashlib.sha256(np.ascontiguousarray(Θ).tobytes()).hexdigest(),
+        status=np.array([0 if s.status == "solved" else 1 for s in sols], dtype=np.int32),
+        x=np.stack([s.x for s in sols], axis=1), y=np.stack([s.y for s in sols], axis=1),
+        s=np.stack([s.s for s in sols], axis=1), eps=np.array([s.eps for s in sols]),
+        outer_iters=np.array([s.outer_iters for s in sols], dtype=np.int32),
+        newton_steps=np.array([s.newton_steps for s in sols], dtype=np.int32))
 
 
 if __name__ == "__main__":

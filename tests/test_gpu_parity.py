@@ -243,6 +243,23 @@ def test_against_golden_batches(name, builder):
             assert rel_err(got[:, b], want[:, b]) <= RTOL
 
 
+def test_against_golden_qp100():
+    """cfg2 at the benchmark's size against the Python oracle's frozen trajectory (θ regenerated from the seed; the
+    fixture holds its SHA-256).  The GPU factorises by LDLᵀ, the oracle by pivoted sparse LU."""
+    import hashlib
+    d = np.load(os.path.join(GOLD, "random_qp_100x100_seed5.npz"))
+    Θ = problems.random_qp_thetas(int(d["B"]), seed=int(d["seed"]))
+    if hashlib.sha256(np.ascontiguousarray(Θ).tobytes()).hexdigest() != str(d["theta_sha256"]):
+        pytest.skip("numpy's generator stream differs from the one the fixture was made with")
+    sol = solve(InteriorPoint(), problems.random_qp(100, 100), Θ, tol=float(d["tol"]))
+    np.testing.assert_array_equal(sol.status, d["status"])
+    assert np.all(np.abs(sol.newton_steps - d["newton_steps"]) <= 1)
+    assert np.all(np.abs(sol.outer_iters - d["outer_iters"]) <= 1)
+    for got, want in ((sol.x, d["x"]), (sol.y, d["y"]), (sol.s, d["s"])):
+        for b in range(want.shape[1]):
+            assert rel_err(got[:, b], want[:, b]) <= RTOL
+
+
 def test_against_golden_small(readme_mcp, clamp_game):
     with open(os.path.join(GOLD, "small.json")) as f:
         g = json.load(f)

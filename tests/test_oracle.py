@@ -168,6 +168,23 @@ def test_golden_batches_python_and_c(name, builder, kw):
         assert np.max(np.abs(c.s[:, b] - d["s"][:, b])) / scale(d["s"][:, b]) < 1e-6
 
 
+def test_golden_qp100_c_oracle():
+    """cfg2 at the benchmark's size: θ regenerated from the seed (guarded by its SHA-256), the C restatement against the
+    Python oracle's frozen trajectory."""
+    import hashlib
+    d = np.load(os.path.join(GOLD, "random_qp_100x100_seed5.npz"))
+    Θ = problems.random_qp_thetas(int(d["B"]), seed=int(d["seed"]))
+    assert hashlib.sha256(np.ascontiguousarray(Θ).tobytes()).hexdigest() == str(d["theta_sha256"])
+    mcp = problems.random_qp(100, 100)
+    c = CO.solve_batch(mcp.ir, Θ, tol=float(d["tol"]))
+    np.testing.assert_array_equal(c.status, d["status"])
+    np.testing.assert_array_equal(c.newton_steps, d["newton_steps"])
+    np.testing.assert_array_equal(c.outer_iters, d["outer_iters"])
+    for k in ("x", "y", "s"):
+        got, want = getattr(c, k), d[k]
+        assert np.max(np.abs(got - want)) / max(1.0, np.max(np.abs(want))) < 1e-9
+
+
 def test_c_oracle_readme_batch_and_threads():
     g = _small()["readme_qp_batch"]
     ir = problems.readme_qp().ir
