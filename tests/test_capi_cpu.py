@@ -259,6 +259,23 @@ def test_hot_tables_move_to_shared_memory_when_it_costs_no_instance(monkeypatch,
     assert _macros(capi.Handle(problems.readme_qp().ir, capi.COMPILE_ONLY).source())["HOT_SMEM"] == "0"
 
 
+@pytest.mark.parametrize("mk", [lambda: problems.lane_change_game(horizon=4).mcp, lambda: problems.lane_change_game(horizon=16).mcp,
+                                lambda: problems.masked_game(3, 6).mcp, lambda: problems.masked_game(2, 12).mcp])
+def test_hot_tables_never_cost_a_build(mk, monkeypatch, tmp_path):
+    """Whatever the planner decides about the shared-memory tables for a banded problem of another size, the module must
+    still compile (ptxas rejects > 48 KB of static shared memory) and keep the instances per CTA it has without them."""
+    monkeypatch.setenv("MCPB200_CACHE_DIR", str(tmp_path))
+    mcp = mk()
+    h = capi.Handle(mcp.ir, capi.COMPILE_ONLY)
+    with_hot, hot = h.info()["instances_per_cta"], _macros(h.source())["HOT_SMEM"]
+    h.close()
+    monkeypatch.setenv("MCPB200_HOT_SMEM", "0")
+    h = capi.Handle(mcp.ir, capi.COMPILE_ONLY)
+    assert _macros(h.source())["HOT_SMEM"] == "0"
+    assert h.info()["instances_per_cta"] == with_hot, hot
+    h.close()
+
+
 def test_split_units_respect_the_kernels_register_budget(monkeypatch, tmp_path):
     """Separately compiled evaluation units do not see the kernels' launch bounds; the runtime caps their registers
     so that nvJitLink accepts them (a 256-thread, 2-CTA/SM dense kernel may call only ≤128-register functions)."""
