@@ -251,75 +251,94 @@ def other_workloads(local: int, fp64_peak: float, hbm_gbs: float, reps: int = 3)
                           "d2h_bytes_per_step": B * ((nx + 2 * ny) * 8 + 28), "ms_per_step": dt * 1e3}
         return ent, sol, θd
 
-    # cfg1 — README QP, 2^20 θ, defaults (tol 1e-4) and tol 1e-6
-    mcp = problems.readme_qp()
-    Θ = problems.readme_qp_thetas(1 << 20, seed=1)
-    out["cfg1_readme_qp_tol1e-4"], _, _ = solve_entry(mcp, Θ, 1e-4)
-    out["cfg1_readme_qp_tol1e-6"], _, _ = solve_entry(mcp, Θ, 1e-6, e2e=False)
-    # cfg2 — random convex QP 100×100: cold, then the θ sweep (ϕ ← ϕ + 0.01·N(0,1)) warm-started from the cold solution
-    mcp = problems.random_qp(100, 100)
-    Bq = 1 << 15   # (r1's batch; ≈ 35 ms of the call is the pass-1 tail of the never-converging instances, whatever the batch)
-    Θ = problems.random_qp_thetas(Bq, seed=1)
-    cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1; roofline credits the reference algorithm's flops (dense LU + dense "
-                                                   "Schur product, SURVEY.md §8d) — the kernel executes fewer: LDLᵀ for symmetric G_x, Schur terms "
-                                                   "that are zero in value skipped (DESIGN.md §8)")
-    out["cfg2_random_qp_cold"] = cold
-    g = torch.Generator(device=dev)
-    g.manual_seed(7)
-    θ2 = θd.clone()
-    θ2[:, -100:] += 0.01 * torch.randn((Bq, 100), dtype=torch.float64, device=dev, generator=g)
-    x0, y0 = sol["x"].clone(), sol["y"].clamp_min(1e-3)
-    h = _handle(mcp)
-    warm = {k: torch.empty_like(v) for k, v in sol.items()}
-    dopts = capi.default_opts(tol=TOL)
+    def guard(label, fn):   # one config failing (memory, a box without enough host RAM for 5 GB of pinned θ) must not cost the others
+        try:
+            fn()
+        except Exception as ex:
+            out[label + "_error"] = f"{type(ex).__name__}: {ex}"
+            torch.cuda.empty_cache()
 
-    def warm_step():
-        h.check(h._lib.mcpb200_solve_batched_device(
-            h.raw, Bq, θ2.data_ptr(), x0.data_ptr(), y0.data_ptr(), None, C.byref(dopts), warm["x"].data_ptr(), warm["y"].data_ptr(),
-            warm["s"].data_ptr(), warm["kkt"].data_ptr(), warm["eps"].data_ptr(), warm["outer"].data_ptr(), warm["status"].data_ptr(),
-            warm["steps"].data_ptr(), C.c_void_p(stream.cuda_stream)))
-    ms = _time_device(warm_step, stream, reps)
-    tm, info = h.timing(), h.info()
-    flops = info["flops_per_newton_step_band"] * tm["newton_steps"]
-    out["cfg2_random_qp_warm_sweep"] = {
-        "batch": Bq, "tol": TOL, "value": int(tm["solved"]) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": tm["kernel_ms"],
-        "solved_fraction": int(tm["solved"]) / Bq, "newton_steps": int(tm["newton_steps"]),
-        "newton_steps_cold": cold["newton_steps"],
-        "roofline": {"bound": "fp64", "achieved": flops / (tm["kernel_ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": flops / (tm["kernel_ms"] * 1e-3) / 1e12 / fp64_peak},
-        "note": "same M, A, b; ϕ perturbed by 0.01·N(0,1); x₀, y₀ = cold solution (y₀ clamped ≥ 1e-3), s₀ = 1, ϵ restarts at 1 "
-                "(src/solver.jl:41,67)"}
-    del θd, θ2, sol, warm, x0, y0
-    torch.cuda.empty_cache()
-    # cfg5 — lane-change sensitivities: VJP (adjoint kernel) and the full Jacobian ∂z/∂θ (10 right-hand sides)
-    mcp = problems.lane_change_game().mcp
-    h = _handle(mcp)
-    nx, ny, nt = mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension
-    Bs = 1 << 14
-    θd = torch.from_numpy(np.ascontiguousarray(problems.lane_change_thetas(Bs, seed=5, moving=True).T)).to(dev)
-    sol = torch_api.solve_device(mcp, θd, tol=TOL)
-    zbar = torch.cat([2 * sol["x"], 2 * sol["y"], torch.zeros_like(sol["s"])], dim=1).contiguous()
-    ms = _time_device(lambda: torch_api.pullback_device(mcp, θd, sol["x"], sol["y"], sol["s"], sol["eps"], zbar), stream, reps)
-    tm = h.timing()
-    out["cfg5_lane_change_vjp"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "VJPs/s", "ms_per_step": ms,
-                                   "kernel_ms": tm["kernel_ms"], "note": "adjoint mode: one solve with Cᵀ per instance (src/AutoDiff.jl:59-76)"}
-    jac = torch.empty((Bs, nt, nx + 2 * ny), dtype=torch.float64, device=dev)
+    def cfg1():
+        # cfg1 — README QP, 2^20 θ, defaults (tol 1e-4) and tol 1e-6
+        mcp = problems.readme_qp()
+        Θ = problems.readme_qp_thetas(1 << 20, seed=1)
+        out["cfg1_readme_qp_tol1e-4"], _, _ = solve_entry(mcp, Θ, 1e-4)
+        out["cfg1_readme_qp_tol1e-6"], _, _ = solve_entry(mcp, Θ, 1e-6, e2e=False)
 
-    def jac_step():
-        h.check(h._lib.mcpb200_sensitivities_device(h.raw, Bs, θd.data_ptr(), sol["x"].data_ptr(), sol["y"].data_ptr(), sol["s"].data_ptr(),
-                                                    sol["eps"].data_ptr(), jac.data_ptr(), None, None, 0, None, None, None,
-                                                    C.c_void_p(stream.cuda_stream)))
-    ms = _time_device(jac_step, stream, reps)
-    tm = h.timing()
-    out["cfg5_lane_change_jacobian"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "Jacobians/s", "ms_per_step": ms,
-                                        "kernel_ms": tm["kernel_ms"], "note": "∂z/∂θ, 700×10 per instance (src/AutoDiff.jl:18-40)"}
-    del jac, zbar, sol, θd
-    torch.cuda.empty_cache()
-    # cfg4 — masked game N = 4, H = 30: all 8 ego masks × 256 scenarios, stay-at-rest x₀, tol 1e-4 (the application's settings)
-    mcp = problems.masked_game(4, 30).mcp
-    Θ = problems.masked_game_thetas(8192, 4, seed=1)
-    x0 = torch.from_numpy(np.ascontiguousarray(problems.masked_game_x0(Θ, 4, 30).T)).to(dev)
-    out["cfg4_masked_game_n4"], _, _ = solve_entry(mcp, Θ, 1e-4, x0=x0, e2e=False, note="8 ego masks × 1024 scenarios, x₀ = stay-at-rest rollout")
+    def cfg2():
+        # cfg2 — random convex QP 100×100: cold, then the θ sweep (ϕ ← ϕ + 0.01·N(0,1)) warm-started from the cold solution
+        mcp = problems.random_qp(100, 100)
+        Bq = 1 << 15   # (r1's batch; ≈ 35 ms of the call is the pass-1 tail of the never-converging instances, whatever the batch)
+        Θ = problems.random_qp_thetas(Bq, seed=1)
+        cold, sol, θd = solve_entry(mcp, Θ, TOL, note="cold start x₀=0, y₀=s₀=1; roofline credits the reference algorithm's flops (dense LU + dense "
+                                                       "Schur product, SURVEY.md §8d) — the kernel executes fewer: LDLᵀ for symmetric G_x, Schur terms "
+                                                       "that are zero in value skipped (DESIGN.md §8)")
+        out["cfg2_random_qp_cold"] = cold
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        θ2 = θd.clone()
+        θ2[:, -100:] += 0.01 * torch.randn((Bq, 100), dtype=torch.float64, device=dev, generator=g)
+        x0, y0 = sol["x"].clone(), sol["y"].clamp_min(1e-3)
+        h = _handle(mcp)
+        warm = {k: torch.empty_like(v) for k, v in sol.items()}
+        dopts = capi.default_opts(tol=TOL)
+
+        def warm_step():
+            h.check(h._lib.mcpb200_solve_batched_device(
+                h.raw, Bq, θ2.data_ptr(), x0.data_ptr(), y0.data_ptr(), None, C.byref(dopts), warm["x"].data_ptr(), warm["y"].data_ptr(),
+                warm["s"].data_ptr(), warm["kkt"].data_ptr(), warm["eps"].data_ptr(), warm["outer"].data_ptr(), warm["status"].data_ptr(),
+                warm["steps"].data_ptr(), C.c_void_p(stream.cuda_stream)))
+        ms = _time_device(warm_step, stream, reps)
+        tm, info = h.timing(), h.info()
+        flops = info["flops_per_newton_step_band"] * tm["newton_steps"]
+        out["cfg2_random_qp_warm_sweep"] = {
+            "batch": Bq, "tol": TOL, "value": int(tm["solved"]) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel_ms": tm["kernel_ms"],
+            "solved_fraction": int(tm["solved"]) / Bq, "newton_steps": int(tm["newton_steps"]),
+            "newton_steps_cold": cold["newton_steps"],
+            "roofline": {"bound": "fp64", "achieved": flops / (tm["kernel_ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": flops / (tm["kernel_ms"] * 1e-3) / 1e12 / fp64_peak},
+            "note": "same M, A, b; ϕ perturbed by 0.01·N(0,1); x₀, y₀ = cold solution (y₀ clamped ≥ 1e-3), s₀ = 1, ϵ restarts at 1 "
+                    "(src/solver.jl:41,67)"}
+        del θd, θ2, sol, warm, x0, y0
+        torch.cuda.empty_cache()
+
+    def cfg5():
+        # cfg5 — lane-change sensitivities: VJP (adjoint kernel) and the full Jacobian ∂z/∂θ (10 right-hand sides)
+        mcp = problems.lane_change_game().mcp
+        h = _handle(mcp)
+        nx, ny, nt = mcp.unconstrained_dimension, mcp.constrained_dimension, mcp.parameter_dimension
+        Bs = 1 << 14
+        θd = torch.from_numpy(np.ascontiguousarray(problems.lane_change_thetas(Bs, seed=5, moving=True).T)).to(dev)
+        sol = torch_api.solve_device(mcp, θd, tol=TOL)
+        zbar = torch.cat([2 * sol["x"], 2 * sol["y"], torch.zeros_like(sol["s"])], dim=1).contiguous()
+        ms = _time_device(lambda: torch_api.pullback_device(mcp, θd, sol["x"], sol["y"], sol["s"], sol["eps"], zbar), stream, reps)
+        tm = h.timing()
+        out["cfg5_lane_change_vjp"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "VJPs/s", "ms_per_step": ms,
+                                       "kernel_ms": tm["kernel_ms"], "note": "adjoint mode: one solve with Cᵀ per instance (src/AutoDiff.jl:59-76)"}
+        jac = torch.empty((Bs, nt, nx + 2 * ny), dtype=torch.float64, device=dev)
+
+        def jac_step():
+            h.check(h._lib.mcpb200_sensitivities_device(h.raw, Bs, θd.data_ptr(), sol["x"].data_ptr(), sol["y"].data_ptr(), sol["s"].data_ptr(),
+                                                        sol["eps"].data_ptr(), jac.data_ptr(), None, None, 0, None, None, None,
+                                                        C.c_void_p(stream.cuda_stream)))
+        ms = _time_device(jac_step, stream, reps)
+        tm = h.timing()
+        out["cfg5_lane_change_jacobian"] = {"batch": Bs, "value": Bs / (ms * 1e-3), "unit": "Jacobians/s", "ms_per_step": ms,
+                                            "kernel_ms": tm["kernel_ms"], "note": "∂z/∂θ, 700×10 per instance (src/AutoDiff.jl:18-40)"}
+        del jac, zbar, sol, θd
+        torch.cuda.empty_cache()
+
+    def cfg4():
+        # cfg4 — masked game N = 4, H = 30: all 8 ego masks × 256 scenarios, stay-at-rest x₀, tol 1e-4 (the application's settings)
+        mcp = problems.masked_game(4, 30).mcp
+        Θ = problems.masked_game_thetas(8192, 4, seed=1)
+        x0 = torch.from_numpy(np.ascontiguousarray(problems.masked_game_x0(Θ, 4, 30).T)).to(dev)
+        out["cfg4_masked_game_n4"], _, _ = solve_entry(mcp, Θ, 1e-4, x0=x0, e2e=False, note="8 ego masks × 1024 scenarios, x₀ = stay-at-rest rollout")
+
+    guard("cfg1_readme_qp", cfg1)
+    guard("cfg2_random_qp", cfg2)
+    guard("cfg5_lane_change", cfg5)
+    guard("cfg4_masked_game_n4", cfg4)
     return out
 
 
